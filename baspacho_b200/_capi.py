@@ -29,7 +29,7 @@ DECLARED_SYMBOLS = [
     "last_error", "version", "create_solver", "create_solver_from_skel", "destroy_solver", "solver_query",
     "solver_array", "densify", "damp", "block_offset", "work_estimate", "set_stream", "set_fused", "factor",
     "factor_batched", "solve", "solve_batched", "add_mv_from", "pseudo_factor_from", "do_elimination",
-    "factor_solve_host", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
+    "factor_solve_host", "dev_gemm_nt", "dev_potrf", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
     "pattern_free", "random_data", "fill_reducing_permutation",
 ]
 
@@ -73,6 +73,9 @@ class CApi:
         f("pseudo_factor_from", C.c_int, [vp, C.c_int, vp, c_i64])
         f("do_elimination", C.c_int, [vp, C.c_int, vp, C.c_int])
         f("factor_solve_host", C.c_int, [vp, C.c_int, vp, vp, vp, c_i64, C.c_int])
+        if prefix == "bspb200_":
+            f("dev_gemm_nt", C.c_int, [C.c_int, c_i64, c_i64, c_i64, C.c_double, vp, c_i64, vp, c_i64, C.c_double, vp, c_i64, C.c_int, vp])
+            f("dev_potrf", C.c_int, [C.c_int, c_i64, c_i64, vp, c_i64, vp])
         f("launch_count", c_i64, [])
         f("gen_pattern", C.c_int, [C.c_int, c_dblp, C.c_int, c_i64, c_i64, c_i64, C.POINTER(vp)])
         f("pattern_order", c_i64, [vp])

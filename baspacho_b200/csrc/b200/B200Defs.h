@@ -1,0 +1,104 @@
+// Common definitions of the B200 (sm_100a) backend: error handling (exceptions, never abort: the
+// reference's cuCHECK aborts the process, CudaDefs.h:27-65), RAII device buffers (role of the
+// reference's DevMirror, CudaDefs.h:75-128), the batch-aware data reference passed to every kernel
+// (role of the reference's Plain/Batched policies, MatOpsCuda.cu:345-368) and the launch counter.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace BaSpaCho {
+namespace b200 {
+
+[[noreturn]] inline void cudaFail(cudaError_t e, const char* what, const char* file, int line) {
+  std::stringstream ss;
+  ss << "[" << file << ":" << line << "] CUDA error in " << what << ": " << cudaGetErrorString(e);
+  throw std::runtime_error(ss.str());
+}
+
+#define B200_CUDA(call)                                                          \
+  do {                                                                           \
+    cudaError_t b200_err_ = (call);                                              \
+    if (b200_err_ != cudaSuccess) ::BaSpaCho::b200::cudaFail(b200_err_, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// number of kernels launched by this library (bench.py "gpu_launches")
+std::atomic<int64_t>& launchCounter();
+inline void countLaunch(int64_t n = 1) { launchCounter().fetch_add(n, std::memory_order_relaxed); }
+
+#define B200_LAUNCH_CHECK()                 \
+  do {                                      \
+    ::BaSpaCho::b200::countLaunch();        \
+    B200_CUDA(cudaGetLastError());          \
+  } while (0)
+
+// One matrix (`one`) or a batch of identically structured matrices (`many`: DEVICE array of `batch`
+// device pointers). Kernels take the batch index from blockIdx.z.
+template <typename T>
+struct Mats {
+  T* one = nullptr;
+  T* const* many = nullptr;
+  int batch = 1;
+  __host__ __device__ T* at(int b) const { return many ? many[b] : one; }
+};
+
+// Per-batch-item workspace: item b lives at base + b * stride.
+template <typename T>
+struct Work {
+  T* base = nullptr;
+  int64_t stride = 0;
+  __host__ __device__ T* at(int b) const { return base + (int64_t)b * stride; }
+};
+
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { resize(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr, o.n_ = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_, n_ = o.n_;
+      o.p_ = nullptr, o.n_ = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+
+  void resize(size_t n) {
+    if (n == n_) return;
+    release();
+    if (n) B200_CUDA(cudaMalloc((void**)&p_, n * sizeof(T)));
+    n_ = n;
+  }
+  void ensure(size_t n) {
+    if (n > n_) resize(n);
+  }
+  void upload(const std::vector<T>& v) {
+    resize(v.size());
+    if (!v.empty()) B200_CUDA(cudaMemcpy(p_, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr, n_ = 0;
+  }
+  T* ptr() const { return p_; }
+  size_t size() const { return n_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+inline int ceilDiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace b200
+}  // namespace BaSpaCho

@@ -1,0 +1,90 @@
+// Launch wrappers of the hand-written sm_100a kernels (definitions in DenseKernels.cu, SparseKernels.cu,
+// SolveKernels.cu). Everything is row-major; `Operand` locates a matrix inside the factor data (one
+// pointer or a device array of batch pointers) or inside a per-batch-item workspace.
+#pragma once
+
+#include "B200Defs.h"
+
+namespace BaSpaCho {
+namespace b200 {
+
+template <typename T>
+struct Operand {
+  T* base = nullptr;         // single matrix / workspace base
+  T* const* many = nullptr;  // device array of batch pointers (overrides base)
+  int64_t off = 0;           // element offset added to the selected pointer
+  int64_t bstride = 0;       // workspace: distance between batch items
+  __host__ __device__ T* at(int b) const { return (many ? many[b] : base + (int64_t)b * bstride) + off; }
+};
+
+template <typename T>
+inline Operand<T> opnd(const Mats<T>& m, int64_t off) {
+  Operand<T> o;
+  o.base = m.one, o.many = m.many, o.off = off, o.bstride = 0;
+  return o;
+}
+template <typename T>
+inline Operand<T> opnd(const Work<T>& w, int64_t off) {
+  Operand<T> o;
+  o.base = w.base, o.many = nullptr, o.off = off, o.bstride = w.stride;
+  return o;
+}
+template <typename T>
+inline Operand<T> shifted(Operand<T> o, int64_t delta) {
+  o.off += delta;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------- dense (DenseKernels.cu)
+// C(m x n) = alpha * A(m x k) * B(n x k)^T + beta * C.  lowerOnly: only entries with col <= row are
+// computed/stored (tiles strictly above the diagonal are skipped). double -> DMMA tensor tiles.
+template <typename T>
+void gemmNT(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k, T alpha, Operand<T> A, int64_t lda,
+            Operand<T> B, int64_t ldb, T beta, Operand<T> C, int64_t ldc, bool lowerOnly);
+
+// max diagonal block handled by one CTA (potrfBlock / trsmBlock / trsvBlock)
+template <typename T>
+int maxBlockDim();
+
+// in-place Cholesky of the n x n (n <= maxBlockDim) block, lower triangle, one CTA per batch item
+template <typename T>
+void potrfBlock(cudaStream_t st, int batch, int n, Operand<T> A, int64_t lda);
+
+// X * tril(L)^T = B in place on `rows` rows (L: n x n, n <= maxBlockDim)
+template <typename T>
+void trsmBlock(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B, int64_t ldb);
+
+// Cholesky of the trapezoid: A is (n + rowsBelow) x n row-major (ld), top n x n = diagonal block.
+// Blocked recursively on top of potrfBlock / trsmBlock / gemmNT. rowsBelow = 0 -> plain potrf.
+template <typename T>
+void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld);
+
+// X * tril(L)^T = B for any n (blocked): L n x n (ldl), B rows x n (ldb)
+template <typename T>
+void trsmAny(cudaStream_t st, int batch, int64_t n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B, int64_t ldb);
+
+// ---------------------------------------------------------------------------------- vectors (SolveKernels.cu)
+// Vectors are column-major (rows x nRHS, leading dimension ldc).
+// tril(L) X = C (transposed=false) or tril(L)^T X = C (transposed=true), L n x n row-major (ldl), any n
+template <typename T>
+void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
+             bool transposed);
+
+// out[i * outRowStride + c * outColStride] (+)= alpha * sum_q M[i][q] * X[c * ldx + q]   (M rows x cols, ldm)
+// (tmp row-major rows x nRHS: strides (nRHS, 1); a column-major vector: strides (1, ld))
+template <typename T>
+void gemvRows(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm, Operand<T> X,
+              int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate);
+
+// X[c * ldx + q] += alpha * sum_i M[i][q] * in[i * inRowStride + c * inColStride]
+template <typename T>
+void gemvColsT(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm,
+               Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS);
+
+// y(col-major ldy)[0..n) += alpha * sym(M) * x(col-major ldx)[0..n), M n x n lower-stored row-major (ldm = n)
+template <typename T>
+void symmLower(cudaStream_t st, int batch, int64_t n, T alpha, Operand<T> M, Operand<T> X, int64_t ldx, Operand<T> Y,
+               int64_t ldy, int nRHS);
+
+}  // namespace b200
+}  // namespace BaSpaCho

@@ -1,0 +1,385 @@
+// The B200 backend behind the reference's operator interface (host/MatOps.h == reference MatOps.h):
+// b200Ops() -> B200SymbolicCtx -> B200SymElimCtx / B200NumericCtx<T> / B200SolveCtx<T>, for
+// T in {double, float, std::vector<double*>, std::vector<float*>} - what reference MatOpsCuda.cu:55-1471
+// provides with cuBLAS/cuSOLVER + 11 SIMT kernels, rebuilt on hand-written sm_100a kernels:
+//   * every op runs on an explicit stream (reference: stream 0 only, MatOpsCuda.cu:58-62);
+//   * workspaces live in the symbolic context and are reused across factor()/solve() calls
+//     (reference: cudaMalloc per call, MatOpsCuda.cu:410-414, 1016-1018);
+//   * no host<->device traffic inside factor()/solve() except the batch pointer array when it changes
+//     (reference: numSpans*8 bytes H2D per lump in prepareAssemble :471-481, pointer arrays before every op);
+//   * errors are std::runtime_error, never abort() (reference: CudaDefs.h:27-65).
+#include <cstring>
+#include <memory>
+#include "../host/DebugMacros.h"
+#include "../host/MatOps.h"
+#include "B200Kernels.h"
+#include "B200Plan.h"
+#include "B200Sparse.h"
+
+namespace BaSpaCho {
+namespace {
+
+using namespace b200;
+using std::vector;
+
+thread_local cudaStream_t tlsSyncStream = nullptr;
+struct B200SyncOps {
+  static void sync() { cudaStreamSynchronize(tlsSyncStream); }
+};
+
+struct B200SymElimCtx : SymElimCtx {
+  ElimPlan host;  // index vectors are released after upload; scalars stay
+  DevBuf<int64_t> dstOff, rowChainOff;
+  DevBuf<int32_t> dstStride, dstTaskPtr, rowPtr, rowChainCol;
+  DevBuf<int16_t> dstRows, dstCols, rowChainK;
+  DevBuf<uint32_t> taskA, taskB;
+  DevBuf<uint16_t> taskK;
+  DevElimPlan dev;
+};
+
+struct B200SymbolicCtx : SymbolicCtx {
+  B200SymbolicCtx(const CoalescedBlockMatrixSkel& s, const vector<int64_t>& permutation) : skel(s) {
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0)
+      throw std::runtime_error(std::string("BaSpaCho-B200: no usable CUDA device (") +
+                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                               "); this library has no CPU fallback");
+    dSpanStart.upload(s.spanStart);
+    dSpanToLump.upload(s.spanToLump);
+    dLumpStart.upload(s.lumpStart);
+    dLumpToSpan.upload(s.lumpToSpan);
+    dSpanOffsetInLump.upload(s.spanOffsetInLump);
+    dChainColPtr.upload(s.chainColPtr);
+    dChainRowSpan.upload(s.chainRowSpan);
+    dChainData.upload(s.chainData);
+    dChainRowsTillEnd.upload(s.chainRowsTillEnd);
+    dBoardColPtr.upload(s.boardColPtr);
+    dBoardRowLump.upload(s.boardRowLump);
+    dBoardChainColOrd.upload(s.boardChainColOrd);
+    dPermutation.upload(permutation);
+    dsk.spanStart = dSpanStart.ptr(), dsk.spanToLump = dSpanToLump.ptr(), dsk.lumpStart = dLumpStart.ptr();
+    dsk.lumpToSpan = dLumpToSpan.ptr(), dsk.spanOffsetInLump = dSpanOffsetInLump.ptr();
+    dsk.chainColPtr = dChainColPtr.ptr(), dsk.chainRowSpan = dChainRowSpan.ptr(), dsk.chainData = dChainData.ptr();
+    dsk.chainRowsTillEnd = dChainRowsTillEnd.ptr(), dsk.boardColPtr = dBoardColPtr.ptr();
+    dsk.boardRowLump = dBoardRowLump.ptr(), dsk.boardChainColOrd = dBoardChainColOrd.ptr();
+    dsk.numSpans = s.numSpans(), dsk.numLumps = s.numLumps();
+    spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
+    // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
+    potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
+    solveSparseLStat.enabled = solveSparseLtStat.enabled = pseudoFactorStat.enabled = symmStat.enabled = false;
+    solveLStat.enabled = solveLtStat.enabled = solveGemvStat.enabled = solveGemvTStat.enabled = false;
+    solveAssVStat.enabled = solveAssVTStat.enabled = false;
+  }
+
+  void setStream(void* s) override {
+    stream = (cudaStream_t)s;
+    tlsSyncStream = stream;
+  }
+
+  PermutedCoalescedAccessor deviceAccessor() override {
+    PermutedCoalescedAccessor a;
+    a.init(dsk.spanStart, dsk.spanToLump, dsk.lumpStart, dsk.spanOffsetInLump, dsk.chainColPtr, dsk.chainRowSpan,
+           dsk.chainData, dPermutation.ptr());
+    return a;
+  }
+
+  SymElimCtxPtr prepareElimination(int64_t lumpsBegin, int64_t lumpsEnd) override {
+    auto e = std::make_unique<B200SymElimCtx>();
+    e->elimStat.enabled = false;
+    ElimPlan& p = e->host;
+    p = buildElimPlan(skel, lumpsBegin, lumpsEnd);
+    e->dstOff.upload(p.dstOff), e->dstStride.upload(p.dstStride), e->dstRows.upload(p.dstRows);
+    e->dstCols.upload(p.dstCols), e->dstTaskPtr.upload(p.dstTaskPtr), e->taskA.upload(p.taskA);
+    e->taskB.upload(p.taskB), e->taskK.upload(p.taskK), e->rowPtr.upload(p.rowPtr);
+    e->rowChainOff.upload(p.rowChainOff), e->rowChainCol.upload(p.rowChainCol), e->rowChainK.upload(p.rowChainK);
+    DevElimPlan& d = e->dev;
+    d.lumpsBegin = lumpsBegin, d.lumpsEnd = lumpsEnd, d.spanRowBegin = p.spanRowBegin;
+    d.uniformLumpSize = p.uniformLumpSize;
+    d.numDst = p.numDst(), d.maxDstElems = p.maxDstElems;
+    d.dstOff = e->dstOff.ptr(), d.dstStride = e->dstStride.ptr(), d.dstRows = e->dstRows.ptr();
+    d.dstCols = e->dstCols.ptr(), d.dstTaskPtr = e->dstTaskPtr.ptr(), d.taskA = e->taskA.ptr();
+    d.taskB = e->taskB.ptr(), d.taskK = e->taskK.ptr();
+    d.numRowSpans = (int64_t)p.rowPtr.size() - 1, d.maxRowSpanSize = p.maxRowSpanSize;
+    d.rowPtr = e->rowPtr.ptr(), d.rowChainOff = e->rowChainOff.ptr(), d.rowChainCol = e->rowChainCol.ptr();
+    d.rowChainK = e->rowChainK.ptr();
+    // keep only the scalars on the host
+    for (auto* v : {&p.dstOff, &p.rowChainOff}) vector<int64_t>().swap(*v);
+    for (auto* v : {&p.dstStride, &p.dstTaskPtr, &p.rowPtr, &p.rowChainCol}) vector<int32_t>().swap(*v);
+    for (auto* v : {&p.dstRows, &p.dstCols, &p.rowChainK}) vector<int16_t>().swap(*v);
+    for (auto* v : {&p.taskA, &p.taskB}) vector<uint32_t>().swap(*v);
+    vector<uint16_t>().swap(p.taskK);
+    return SymElimCtxPtr(e.release());
+  }
+
+  NumericCtxBase* createNumericCtxForType(std::type_index tIdx, int64_t tempBufSize, int batchSize) override;
+  SolveCtxBase* createSolveCtxForType(std::type_index tIdx, int nRHS, int batchSize) override;
+
+  // grow-only scratch shared by the numeric / solve contexts (one host thread per Solver, as in the reference)
+  void* scratch(size_t bytes) {
+    if (bytes > scratchBytes.size()) {
+      B200_CUDA(cudaStreamSynchronize(stream));
+      scratchBytes.resize(bytes + bytes / 8);
+    }
+    return scratchBytes.ptr();
+  }
+
+  const CoalescedBlockMatrixSkel& skel;
+  cudaStream_t stream = nullptr;
+  DevSkel dsk;
+  DevBuf<int64_t> dSpanStart, dSpanToLump, dLumpStart, dLumpToSpan, dSpanOffsetInLump, dChainColPtr, dChainRowSpan,
+      dChainData, dChainRowsTillEnd, dBoardColPtr, dBoardRowLump, dBoardChainColOrd, dPermutation;
+  DevBuf<int64_t> spanToChainOffset;
+  DevBuf<unsigned char> scratchBytes;
+};
+
+// device array of batch pointers, re-uploaded only when the host vector changes
+template <typename T>
+struct PtrBatch {
+  DevBuf<T*> dev;
+  vector<T*> last;
+  Mats<T> get(const vector<T*>* v, cudaStream_t st) {
+    if (*v != last) {
+      dev.ensure(v->size());
+      B200_CUDA(cudaMemcpyAsync(dev.ptr(), v->data(), v->size() * sizeof(T*), cudaMemcpyHostToDevice, st));
+      last = *v;
+    }
+    Mats<T> m;
+    m.many = dev.ptr(), m.batch = (int)v->size();
+    return m;
+  }
+};
+
+template <typename TT>
+struct MatsOf {
+  using T = TT;
+  Mats<T> get(const T* data, cudaStream_t) {
+    Mats<T> m;
+    m.one = const_cast<T*>(data);
+    return m;
+  }
+};
+template <typename T_>
+struct MatsOf<vector<T_*>> {
+  using T = T_;
+  PtrBatch<T> ptrs;
+  Mats<T> get(const vector<T*>* data, cudaStream_t st) { return ptrs.get(data, st); }
+};
+
+template <typename TT>
+struct B200NumericCtx : NumericCtx<TT> {
+  using T = BaseType<TT>;
+
+  B200NumericCtx(B200SymbolicCtx& s, int64_t tempBufSize, int batchSize)
+      : sym(s), skel(s.skel), tempSize(tempBufSize), batch(batchSize) {
+    tlsSyncStream = sym.stream;
+  }
+
+  Work<T> temp() {
+    Work<T> w;
+    w.base = (T*)sym.scratch((size_t)std::max<int64_t>(1, tempSize) * batch * sizeof(T));
+    w.stride = tempSize;
+    return w;
+  }
+
+  void pseudoFactorSpans(TT* data, int64_t spanBegin, int64_t spanEnd) override {
+    auto timer = sym.pseudoFactorStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream);
+    b200::pseudoFactorSpans<T>(sym.stream, m.batch, sym.dsk, m, spanBegin, spanEnd);
+  }
+
+  void doElimination(const SymElimCtx& elimData, TT* data, int64_t lumpsBegin, int64_t lumpsEnd) override {
+    const auto* elim = dynamic_cast<const B200SymElimCtx*>(&elimData);
+    BASPACHO_CHECK_NOTNULL(elim);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsBegin, lumpsBegin);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsEnd, lumpsEnd);
+    auto timer = elim->elimStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream);
+    elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, lumpsBegin, lumpsEnd, elim->dev.uniformLumpSize);
+    elimGather<T>(sym.stream, m.batch, elim->dev, m);
+  }
+
+  void potrf(int64_t n, TT* data, int64_t offA) override {
+    auto timer = sym.potrfStat.template instance<B200SyncOps>(sizeof(T) + (batch > 1 ? batch * 100 : 0), n);
+    sym.potrfBiggestN = std::max(sym.potrfBiggestN, n);
+    Mats<T> m = mats.get(data, sym.stream);
+    potrfTrapezoid<T>(sym.stream, m.batch, n, 0, opnd(m, offA), n);
+  }
+
+  void trsm(int64_t n, int64_t k, TT* data, int64_t offA, int64_t offB) override {
+    auto timer = sym.trsmStat.template instance<B200SyncOps>(sizeof(T) + (batch > 1 ? batch * 100 : 0), n, k);
+    Mats<T> m = mats.get(data, sym.stream);
+    trsmAny<T>(sym.stream, m.batch, n, k, opnd(m, offA), n, opnd(m, offB), n);
+  }
+
+  void saveSyrkGemm(int64_t m_, int64_t n, int64_t k, const TT* data, int64_t offset) override {
+    auto timer = sym.sygeStat.template instance<B200SyncOps>(sizeof(T) + (batch > 1 ? batch * 100 : 0), m_, n, k);
+    BASPACHO_CHECK_LE(m_ * n, tempSize);
+    Mats<T> m = mats.get(data, sym.stream);
+    // temp(n x m) = B(n x k) * A(m x k)^T, A = first m rows of B
+    Operand<T> B = opnd(m, offset);
+    gemmNT<T>(sym.stream, m.batch, n, m_, k, T(1), B, k, B, k, T(0), opnd(temp(), 0), m_, false);
+    sym.gemmCalls++;
+  }
+
+  void prepareAssemble(int64_t targetLump) override {
+    int64_t begin = skel.chainColPtr[targetLump];
+    b200::prepareAssemble(sym.stream, sym.dsk, sym.spanToChainOffset.ptr(), begin, skel.chainColPtr[targetLump + 1] - begin);
+  }
+
+  void assemble(TT* data, int64_t rectRowBegin, int64_t dstStride, int64_t srcColDataOffset, int64_t srcRectWidth,
+                int64_t numBlockRows, int64_t numBlockCols) override {
+    auto timer = sym.asmblStat.template instance<B200SyncOps>(sizeof(T) + (batch > 1 ? batch * 100 : 0), numBlockRows,
+                                                              numBlockCols);
+    Mats<T> m = mats.get(data, sym.stream);
+    int64_t numRows = skel.chainRowsTillEnd[srcColDataOffset + numBlockRows - 1] - rectRowBegin;
+    b200::assemble<T>(sym.stream, m.batch, sym.dsk, sym.spanToChainOffset.ptr(), m, temp(), rectRowBegin, dstStride,
+                      srcColDataOffset, srcRectWidth, numBlockRows, numBlockCols, numRows);
+  }
+
+  B200SymbolicCtx& sym;
+  const CoalescedBlockMatrixSkel& skel;
+  int64_t tempSize;
+  int batch;
+  MatsOf<TT> mats;
+};
+
+template <typename TT>
+struct B200SolveCtx : SolveCtx<TT> {
+  using T = BaseType<TT>;
+
+  B200SolveCtx(B200SymbolicCtx& s, int nRHS_, int batchSize) : sym(s), skel(s.skel), nRHS(nRHS_), batch(batchSize) {
+    tlsSyncStream = sym.stream;
+  }
+
+  Work<T> temp() {
+    Work<T> w;
+    w.stride = std::max<int64_t>(1, skel.order() * nRHS);
+    w.base = (T*)sym.scratch((size_t)w.stride * batch * sizeof(T));
+    return w;
+  }
+
+  void sparseElimSolveL(const SymElimCtx& elimData, const TT* data, int64_t lumpsBegin, int64_t lumpsEnd, TT* C,
+                        int64_t ldc) override {
+    auto timer = sym.solveSparseLStat.template instance<B200SyncOps>();
+    const auto* elim = dynamic_cast<const B200SymElimCtx*>(&elimData);
+    BASPACHO_CHECK_NOTNULL(elim);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsBegin, lumpsBegin);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsEnd, lumpsEnd);
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    elimSolveL<T>(sym.stream, m.batch, sym.dsk, elim->dev, m, v, ldc, nRHS);
+  }
+
+  void sparseElimSolveLt(const SymElimCtx& elimData, const TT* data, int64_t lumpsBegin, int64_t lumpsEnd, TT* C,
+                         int64_t ldc) override {
+    auto timer = sym.solveSparseLtStat.template instance<B200SyncOps>();
+    const auto* elim = dynamic_cast<const B200SymElimCtx*>(&elimData);
+    BASPACHO_CHECK_NOTNULL(elim);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsBegin, lumpsBegin);
+    BASPACHO_CHECK_EQ(elim->dev.lumpsEnd, lumpsEnd);
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    elimSolveLt<T>(sym.stream, m.batch, sym.dsk, elim->dev, m, v, ldc, nRHS);
+  }
+
+  void symm(const TT* data, int64_t offM, int64_t n, const TT* C, int64_t offC, int64_t ldc, TT* D, int64_t ldd,
+            T alpha) override {
+    auto timer = sym.symmStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream), x = vecs.get(C, sym.stream), y = vecs2.get(D, sym.stream);
+    symmLower<T>(sym.stream, m.batch, n, alpha, opnd(m, offM), opnd(x, offC), ldc, opnd(y, offC), ldd, nRHS);
+  }
+
+  void solveL(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
+    auto timer = sym.solveLStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false);
+  }
+
+  void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
+    auto timer = sym.solveLtStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true);
+  }
+
+  void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,
+            T alpha) override {
+    auto timer = sym.solveGemvStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(A, sym.stream);
+    gemvRows<T>(sym.stream, m.batch, nRows, nCols, alpha, opnd(m, offM), nCols, opnd(v, offA), lda, opnd(temp(), 0),
+                nRHS, 1, nRHS, false);
+  }
+
+  void gemvT(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, TT* A, int64_t offA, int64_t lda,
+             T alpha) override {
+    auto timer = sym.solveGemvTStat.template instance<B200SyncOps>();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(A, sym.stream);
+    gemvColsT<T>(sym.stream, m.batch, nRows, nCols, alpha, opnd(m, offM), nCols, opnd(temp(), 0), nRHS, 1,
+                 opnd(v, offA), lda, nRHS);
+  }
+
+  int64_t rowsOfChains(int64_t chainColPtr, int64_t numColItems) const {
+    return skel.chainRowsTillEnd[chainColPtr + numColItems - 1] - skel.chainRowsTillEnd[chainColPtr - 1];
+  }
+
+  void assembleVec(int64_t chainColPtr, int64_t numColItems, TT* C, int64_t ldc) override {
+    auto timer = sym.solveAssVStat.template instance<B200SyncOps>();
+    if (numColItems <= 0) return;
+    Mats<T> v = vecs.get(C, sym.stream);
+    b200::assembleVec<T>(sym.stream, v.batch, sym.dsk, temp(), chainColPtr, numColItems,
+                         rowsOfChains(chainColPtr, numColItems), v, ldc, nRHS);
+  }
+
+  void assembleVecT(const TT* C, int64_t ldc, int64_t chainColPtr, int64_t numColItems) override {
+    auto timer = sym.solveAssVTStat.template instance<B200SyncOps>();
+    if (numColItems <= 0) return;
+    Mats<T> v = vecs.get(C, sym.stream);
+    b200::assembleVecT<T>(sym.stream, v.batch, sym.dsk, temp(), chainColPtr, numColItems,
+                          rowsOfChains(chainColPtr, numColItems), v, ldc, nRHS);
+  }
+
+  B200SymbolicCtx& sym;
+  const CoalescedBlockMatrixSkel& skel;
+  int nRHS, batch;
+  MatsOf<TT> mats, vecs, vecs2;
+};
+
+NumericCtxBase* B200SymbolicCtx::createNumericCtxForType(std::type_index tIdx, int64_t tempBufSize, int batchSize) {
+  if (tIdx == std::type_index(typeid(double))) {
+    BASPACHO_CHECK_EQ(batchSize, 1);
+    return new B200NumericCtx<double>(*this, tempBufSize, 1);
+  }
+  if (tIdx == std::type_index(typeid(float))) {
+    BASPACHO_CHECK_EQ(batchSize, 1);
+    return new B200NumericCtx<float>(*this, tempBufSize, 1);
+  }
+  if (tIdx == std::type_index(typeid(vector<double*>)))
+    return new B200NumericCtx<vector<double*>>(*this, tempBufSize, batchSize);
+  if (tIdx == std::type_index(typeid(vector<float*>)))
+    return new B200NumericCtx<vector<float*>>(*this, tempBufSize, batchSize);
+  return nullptr;
+}
+
+SolveCtxBase* B200SymbolicCtx::createSolveCtxForType(std::type_index tIdx, int nRHS, int batchSize) {
+  if (tIdx == std::type_index(typeid(double))) {
+    BASPACHO_CHECK_EQ(batchSize, 1);
+    return new B200SolveCtx<double>(*this, nRHS, 1);
+  }
+  if (tIdx == std::type_index(typeid(float))) {
+    BASPACHO_CHECK_EQ(batchSize, 1);
+    return new B200SolveCtx<float>(*this, nRHS, 1);
+  }
+  if (tIdx == std::type_index(typeid(vector<double*>))) return new B200SolveCtx<vector<double*>>(*this, nRHS, batchSize);
+  if (tIdx == std::type_index(typeid(vector<float*>))) return new B200SolveCtx<vector<float*>>(*this, nRHS, batchSize);
+  return nullptr;
+}
+
+struct B200Ops : Ops {
+  SymbolicCtxPtr createSymbolicCtx(const CoalescedBlockMatrixSkel& skel, const vector<int64_t>& permutation) override {
+    return SymbolicCtxPtr(new B200SymbolicCtx(skel, permutation));
+  }
+};
+
+}  // namespace
+
+OpsPtr b200Ops() { return OpsPtr(new B200Ops); }
+
+}  // namespace BaSpaCho

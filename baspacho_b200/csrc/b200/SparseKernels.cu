@@ -1,0 +1,413 @@
+// Irregular kernels of the B200 backend (sm_100a): sparse elimination, assemble scatter, span-wise
+// pseudo factor, elimination-range triangular solves and the vector gather/scatter of the dense solves.
+// These are HBM-bound index-driven kernels: no tensor cores, coalesced row-wise accesses, fixed summation
+// order (deterministic, no atomics - unlike reference MatOpsCuda.cu:235-331, 883-1012).
+#include "B200Sparse.h"
+
+namespace BaSpaCho {
+namespace b200 {
+namespace {
+
+// in-place lower Cholesky of an s x s row-major block (stride ld) by ONE thread
+// (semantics of reference MathUtils.h:36-63 `cholesky`)
+template <typename T>
+__device__ __forceinline__ void choleskySerial(T* D, int s, int64_t ld) {
+  for (int j = 0; j < s; j++) {
+    T d = D[j * ld + j];
+    for (int q = 0; q < j; q++) d -= D[j * ld + q] * D[j * ld + q];
+    d = sqrt(d);
+    D[j * ld + j] = d;
+    T inv = T(1) / d;
+    for (int i = j + 1; i < s; i++) {
+      T v = D[i * ld + j];
+      for (int q = 0; q < j; q++) v -= D[i * ld + q] * D[j * ld + q];
+      D[i * ld + j] = v * inv;
+    }
+  }
+}
+
+// x <- x * tril(L)^-T for one row x of length s (reference MathUtils.h:66-79 `solveUpperT`)
+template <typename T>
+__device__ __forceinline__ void solveRowSerial(const T* L, int s, int64_t ldl, T* x) {
+  for (int j = 0; j < s; j++) {
+    T v = x[j];
+    for (int q = 0; q < j; q++) v -= x[q] * L[j * ldl + q];
+    x[j] = v / L[j * ldl + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sparse elimination, step 1: one warp per lump. Lane 0 factors the (tiny) diagonal block, then the lanes take
+// the below-diagonal rows (consecutive lanes -> consecutive rows -> coalesced).  S > 0: compile-time width.
+template <typename T, int S>
+__global__ void __launch_bounds__(128) elim_factor_lumps_kernel(DevSkel sk, Mats<T> mats, int64_t lumpsBegin,
+                                                                int64_t lumpsEnd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t lump = lumpsBegin + (int64_t)blockIdx.x * 4 + warp;
+  if (lump >= lumpsEnd) return;
+  T* data = mats.at(blockIdx.z);
+  const int s = S > 0 ? S : (int)(sk.lumpStart[lump + 1] - sk.lumpStart[lump]);
+  const int64_t cb = sk.chainColPtr[lump], ce = sk.chainColPtr[lump + 1];
+  T* D = data + sk.chainData[cb];
+  const int64_t rowsBelow = sk.chainRowsTillEnd[ce - 1] - s;
+  if (lane == 0) choleskySerial(D, s, (int64_t)s);
+  __syncwarp();
+  T* below = D + (int64_t)s * s;
+  if constexpr (S > 0) {
+    T L[S * (S + 1) / 2];
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int q = 0; q <= j; q++) L[j * (j + 1) / 2 + q] = D[j * S + q];
+#pragma unroll
+    for (int j = 0; j < S; j++) L[j * (j + 1) / 2 + j] = T(1) / L[j * (j + 1) / 2 + j];
+    for (int64_t r = lane; r < rowsBelow; r += 32) {
+      T* xr = below + r * S;
+      T x[S];
+#pragma unroll
+      for (int j = 0; j < S; j++) x[j] = xr[j];
+#pragma unroll
+      for (int j = 0; j < S; j++) {
+        T v = x[j];
+#pragma unroll
+        for (int q = 0; q < j; q++) v -= x[q] * L[j * (j + 1) / 2 + q];
+        x[j] = v * L[j * (j + 1) / 2 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < S; j++) xr[j] = x[j];
+    }
+  } else {
+    for (int64_t r = lane; r < rowsBelow; r += 32) solveRowSerial(D, s, (int64_t)s, below + r * s);
+  }
+}
+
+// Sparse elimination, step 2 (destination-major gather): E consecutive threads own one destination block,
+// thread e computes element (e / nc, e % nc) = sum over the block's pair tasks of B[r,:] . A[c,:], then
+// subtracts it from the target once.
+template <typename T>
+__global__ void __launch_bounds__(256) elim_gather_kernel(DevElimPlan p, Mats<T> mats, int E) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t d = gid / E;
+  if (d >= p.numDst) return;
+  T* data = mats.at(blockIdx.z);
+  const int nr = p.dstRows[d], nc = p.dstCols[d];
+  const int tBegin = p.dstTaskPtr[d], tEnd = p.dstTaskPtr[d + 1];
+  T* dst = data + p.dstOff[d];
+  const int64_t stride = p.dstStride[d];
+  for (int e = (int)(gid - d * E); e < nr * nc; e += E) {
+    const int r = e / nc, c = e - r * nc;
+    T acc = 0;
+    for (int t = tBegin; t < tEnd; t++) {
+      const int k = p.taskK[t];
+      const T* __restrict__ a = data + p.taskA[t] + c * k;
+      const T* __restrict__ b = data + p.taskB[t] + r * k;
+      for (int q = 0; q < k; q++) acc += b[q] * a[q];
+    }
+    dst[r * stride + c] -= acc;
+  }
+}
+
+// one CTA (one warp) per span: diagonal block of the span + the rows below it, columns of this span only
+// (reference factor_spans_kernel, MatOpsCuda.cu:188-233)
+template <typename T>
+__global__ void __launch_bounds__(32) pseudo_factor_spans_kernel(DevSkel sk, Mats<T> mats, int64_t spanBegin) {
+  const int64_t span = spanBegin + blockIdx.x;
+  T* data = mats.at(blockIdx.z);
+  const int lane = threadIdx.x;
+  const int64_t lump = sk.spanToLump[span];
+  const int64_t w = sk.lumpStart[lump + 1] - sk.lumpStart[lump];
+  const int s = (int)(sk.spanStart[span + 1] - sk.spanStart[span]);
+  const int64_t ord = span - sk.lumpToSpan[lump];
+  const int64_t cb = sk.chainColPtr[lump], ce = sk.chainColPtr[lump + 1];
+  const int64_t colOff = sk.spanOffsetInLump[span];
+  T* D = data + sk.chainData[cb + ord] + colOff;
+  if (lane == 0) choleskySerial(D, s, w);
+  __syncwarp();
+  const int64_t rowsBelow = sk.chainRowsTillEnd[ce - 1] - sk.chainRowsTillEnd[cb + ord];
+  T* below = D + (int64_t)s * w;  // chains of a lump are consecutive: the next row follows the block
+  for (int64_t r = lane; r < rowsBelow; r += 32) solveRowSerial(D, s, w, below + r * w);
+}
+
+__global__ void prepare_assemble_kernel(DevSkel sk, int64_t* spanToChainOffset, int64_t chainBegin, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) spanToChainOffset[sk.chainRowSpan[chainBegin + i]] = sk.chainData[chainBegin + i];
+}
+
+// index of the chain (relative to `first`) containing row `row` of the column; rowsTillEnd is inclusive-cumulative
+__device__ __forceinline__ int64_t chainOfRow(const int64_t* rowsTillEnd, int64_t count, int64_t row) {
+  int64_t lo = 0, hi = count - 1;  // smallest x with rowsTillEnd[x] > row
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (rowsTillEnd[mid] > row) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// target[rowSpan r][colSpan c] -= temp block for block rows r, block cols c <= r, c < numBlockCols.
+// One thread per scalar of the temp panel: consecutive threads -> consecutive columns (coalesced both sides).
+// (reference assemble_kernel, MatOpsCuda.cu:370-406)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    assemble_kernel(DevSkel sk, const int64_t* __restrict__ spanToChainOffset, Mats<T> mats, Work<T> temp,
+                    int64_t rectRowBegin, int64_t dstStride, int64_t srcColDataOffset, int64_t srcRectWidth,
+                    int64_t numBlockRows, int64_t numBlockCols, int64_t numRows) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= numRows * srcRectWidth) return;
+  const int64_t i = gid / srcRectWidth, j = gid - i * srcRectWidth;
+  const int64_t* rowsTillEnd = sk.chainRowsTillEnd + srcColDataOffset;
+  const int64_t* toSpan = sk.chainRowSpan + srcColDataOffset;
+  const int64_t r = chainOfRow(rowsTillEnd, numBlockRows, i + rectRowBegin);
+  const int64_t c = chainOfRow(rowsTillEnd, numBlockCols, j + rectRowBegin);
+  if (c > r) return;
+  const int64_t rBegin = rowsTillEnd[r - 1] - rectRowBegin, cBegin = rowsTillEnd[c - 1] - rectRowBegin;
+  T* data = mats.at(blockIdx.z);
+  const T* src = temp.at(blockIdx.z);
+  T* dst = data + spanToChainOffset[toSpan[r]] + sk.spanOffsetInLump[toSpan[c]] + (i - rBegin) * dstStride + (j - cBegin);
+  *dst -= src[i * srcRectWidth + j];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// elimination-range solves. Vectors: column-major order x nRHS, leading dimension ldc.
+// (1) per lump diagonal solve: thread per (lump, rhs)
+template <typename T>
+__global__ void __launch_bounds__(128) elim_diag_solve_kernel(DevSkel sk, Mats<T> mats, Mats<T> vecs, int64_t ldc,
+                                                              int nRHS, int64_t lumpsBegin, int64_t lumpsEnd,
+                                                              bool transposed) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t lump = lumpsBegin + gid / nRHS;
+  if (lump >= lumpsEnd) return;
+  const int rhs = (int)(gid % nRHS);
+  const T* __restrict__ data = mats.at(blockIdx.z);
+  T* x = vecs.at(blockIdx.z) + (int64_t)rhs * ldc + sk.lumpStart[lump];
+  const int s = (int)(sk.lumpStart[lump + 1] - sk.lumpStart[lump]);
+  const T* L = data + sk.chainData[sk.chainColPtr[lump]];
+  if (!transposed) {
+    for (int i = 0; i < s; i++) {
+      T v = x[i];
+      for (int q = 0; q < i; q++) v -= L[i * s + q] * x[q];
+      x[i] = v / L[i * s + i];
+    }
+  } else {
+    for (int i = s - 1; i >= 0; i--) {
+      T v = x[i];
+      for (int q = i + 1; q < s; q++) v -= L[q * s + i] * x[q];
+      x[i] = v / L[i * s + i];
+    }
+  }
+}
+
+// (2) forward: one CTA per row span below the range gathers  v[span] -= sum_chains L(span, l) * x_l
+// thread = (element e of the rows x nRHS result, chain group g); groups stride over the row's chains, then a
+// shared-memory reduction over the groups in fixed order.
+template <typename T>
+__global__ void __launch_bounds__(256) elim_gather_solveL_kernel(DevSkel sk, DevElimPlan p, Mats<T> mats,
+                                                                 Mats<T> vecs, int64_t ldc, int nRHS, int E) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* red = reinterpret_cast<T*>(smemRaw);
+  const int64_t rel = blockIdx.x;
+  const int cBegin = p.rowPtr[rel], cEnd = p.rowPtr[rel + 1];
+  if (cBegin == cEnd) return;
+  const int64_t span = rel + p.spanRowBegin;
+  const int64_t r0 = sk.spanStart[span];
+  const int rows = (int)(sk.spanStart[span + 1] - r0);
+  const T* __restrict__ data = mats.at(blockIdx.z);
+  T* C = vecs.at(blockIdx.z);
+  const int G = blockDim.x / E;
+  const int e = threadIdx.x % E, g = threadIdx.x / E;
+  const int nElems = rows * nRHS;
+  // elements beyond E are handled by looping (e, e + E, ...)
+  for (int e0 = 0; e0 < nElems; e0 += E) {
+    const int el = e0 + e;
+    T acc = 0;
+    if (el < nElems && g < G) {
+      const int r = el % rows, rhs = el / rows;
+      for (int c = cBegin + g; c < cEnd; c += G) {
+        const int k = p.rowChainK[c];
+        const T* __restrict__ blk = data + p.rowChainOff[c] + r * k;
+        const T* __restrict__ x = C + (int64_t)rhs * ldc + p.rowChainCol[c];
+        for (int q = 0; q < k; q++) acc += blk[q] * x[q];
+      }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0 && el < nElems) {
+      T tot = 0;
+      for (int gg = 0; gg < G; gg++) tot += red[gg * E + e];
+      const int r = el % rows, rhs = el / rows;
+      C[(int64_t)rhs * ldc + r0 + r] -= tot;
+    }
+    __syncthreads();
+  }
+}
+
+// (3) backward: thread per (lump, rhs): x_l -= sum_chains L(row, l)^T v[row]  (each lump owns its output)
+template <typename T>
+__global__ void __launch_bounds__(128) elim_gather_solveLt_kernel(DevSkel sk, Mats<T> mats, Mats<T> vecs, int64_t ldc,
+                                                                  int nRHS, int64_t lumpsBegin, int64_t lumpsEnd) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t lump = lumpsBegin + gid / nRHS;
+  if (lump >= lumpsEnd) return;
+  const int rhs = (int)(gid % nRHS);
+  const T* __restrict__ data = mats.at(blockIdx.z);
+  T* C = vecs.at(blockIdx.z) + (int64_t)rhs * ldc;
+  const int s = (int)(sk.lumpStart[lump + 1] - sk.lumpStart[lump]);
+  const int64_t c0 = sk.lumpStart[lump];
+  const int64_t first = sk.chainColPtr[lump] + (sk.lumpToSpan[lump + 1] - sk.lumpToSpan[lump]);
+  const int64_t end = sk.chainColPtr[lump + 1];
+  for (int q = 0; q < s; q++) {
+    T acc = C[c0 + q];
+    for (int64_t ch = first; ch < end; ch++) {
+      const int64_t span = sk.chainRowSpan[ch];
+      const int64_t r0 = sk.spanStart[span];
+      const int rows = (int)(sk.spanStart[span + 1] - r0);
+      const T* __restrict__ blk = data + sk.chainData[ch];
+      for (int r = 0; r < rows; r++) acc -= blk[r * s + q] * C[r0 + r];
+    }
+    C[c0 + q] = acc;
+  }
+}
+
+// dense-lump solves: C[rows of chain] += tmp  /  tmp = C[rows of chain]; thread per (row of tmp, rhs)
+template <typename T, bool GATHER>
+__global__ void __launch_bounds__(256) assemble_vec_kernel(DevSkel sk, Work<T> tmp, int64_t chainColPtr,
+                                                           int64_t numColItems, int64_t numRows, Mats<T> vecs,
+                                                           int64_t ldc, int nRHS) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= numRows * nRHS) return;
+  const int64_t i = gid / nRHS;
+  const int rhs = (int)(gid - i * nRHS);
+  const int64_t* rowsTillEnd = sk.chainRowsTillEnd + chainColPtr;
+  const int64_t startRow = rowsTillEnd[-1];
+  const int64_t ch = chainOfRow(rowsTillEnd, numColItems, i + startRow);
+  const int64_t rowOff = rowsTillEnd[ch - 1] - startRow;
+  const int64_t span = sk.chainRowSpan[chainColPtr + ch];
+  T* c = vecs.at(blockIdx.z) + (int64_t)rhs * ldc + sk.spanStart[span] + (i - rowOff);
+  T* t = tmp.at(blockIdx.z) + i * nRHS + rhs;
+  if (GATHER) *t = *c; else *c += *t;
+}
+
+template <typename T, int S>
+void launchFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t b, int64_t e) {
+  elim_factor_lumps_kernel<T, S><<<dim3(ceilDiv(e - b, 4), 1, batch), 128, 0, st>>>(sk, data, b, e);
+}
+
+}  // namespace
+
+template <typename T>
+void elimFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t lumpsBegin, int64_t lumpsEnd,
+                     int uniformLumpSize) {
+  if (lumpsEnd <= lumpsBegin) return;
+  switch (uniformLumpSize) {
+    case 1: launchFactorLumps<T, 1>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    case 2: launchFactorLumps<T, 2>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    case 3: launchFactorLumps<T, 3>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    case 4: launchFactorLumps<T, 4>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    case 5: launchFactorLumps<T, 5>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    case 6: launchFactorLumps<T, 6>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+    default: launchFactorLumps<T, 0>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
+  }
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> data) {
+  if (plan.numDst == 0) return;
+  int E = std::min(plan.maxDstElems, 256);
+  int64_t threads = plan.numDst * E;
+  elim_gather_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(plan, data, E);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void pseudoFactorSpans(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t spanBegin, int64_t spanEnd) {
+  if (spanEnd <= spanBegin) return;
+  pseudo_factor_spans_kernel<T><<<dim3((unsigned)(spanEnd - spanBegin), 1, batch), 32, 0, st>>>(sk, data, spanBegin);
+  B200_LAUNCH_CHECK();
+}
+
+void prepareAssemble(cudaStream_t st, const DevSkel& sk, int64_t* spanToChainOffset, int64_t chainBegin,
+                     int64_t numChains) {
+  if (numChains <= 0) return;
+  prepare_assemble_kernel<<<ceilDiv(numChains, 128), 128, 0, st>>>(sk, spanToChainOffset, chainBegin, numChains);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void assemble(cudaStream_t st, int batch, const DevSkel& sk, const int64_t* spanToChainOffset, Mats<T> data,
+              Work<T> temp, int64_t rectRowBegin, int64_t dstStride, int64_t srcColDataOffset, int64_t srcRectWidth,
+              int64_t numBlockRows, int64_t numBlockCols, int64_t numRows) {
+  int64_t threads = numRows * srcRectWidth;
+  if (threads <= 0) return;
+  assemble_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(
+      sk, spanToChainOffset, data, temp, rectRowBegin, dstStride, srcColDataOffset, srcRectWidth, numBlockRows,
+      numBlockCols, numRows);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void elimSolveL(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> C,
+                int64_t ldc, int nRHS) {
+  int64_t n = (plan.lumpsEnd - plan.lumpsBegin) * nRHS;
+  if (n <= 0) return;
+  elim_diag_solve_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS, plan.lumpsBegin,
+                                                                             plan.lumpsEnd, false);
+  B200_LAUNCH_CHECK();
+  if (plan.numRowSpans <= 0) return;
+  int elems = plan.maxRowSpanSize * nRHS;
+  int E = 1;
+  while (E < elems && E < 32) E *= 2;
+  elim_gather_solveL_kernel<T><<<dim3((unsigned)plan.numRowSpans, 1, batch), 256, 256 * sizeof(T), st>>>(
+      sk, plan, data, C, ldc, nRHS, E);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void elimSolveLt(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> C,
+                 int64_t ldc, int nRHS) {
+  int64_t n = (plan.lumpsEnd - plan.lumpsBegin) * nRHS;
+  if (n <= 0) return;
+  elim_gather_solveLt_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS,
+                                                                                 plan.lumpsBegin, plan.lumpsEnd);
+  B200_LAUNCH_CHECK();
+  elim_diag_solve_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS, plan.lumpsBegin,
+                                                                             plan.lumpsEnd, true);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void assembleVec(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, int64_t chainColPtr, int64_t numColItems,
+                 int64_t numRows, Mats<T> C, int64_t ldc, int nRHS) {
+  int64_t n = numRows * nRHS;
+  if (n <= 0) return;
+  assemble_vec_kernel<T, false><<<dim3(ceilDiv(n, 256), 1, batch), 256, 0, st>>>(sk, tmp, chainColPtr, numColItems,
+                                                                                 numRows, C, ldc, nRHS);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T>
+void assembleVecT(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, int64_t chainColPtr, int64_t numColItems,
+                  int64_t numRows, Mats<T> C, int64_t ldc, int nRHS) {
+  int64_t n = numRows * nRHS;
+  if (n <= 0) return;
+  assemble_vec_kernel<T, true><<<dim3(ceilDiv(n, 256), 1, batch), 256, 0, st>>>(sk, tmp, chainColPtr, numColItems,
+                                                                                numRows, C, ldc, nRHS);
+  B200_LAUNCH_CHECK();
+}
+
+#define B200_INSTANTIATE_SPARSE(T)                                                                                      \
+  template void elimFactorLumps<T>(cudaStream_t, int, const DevSkel&, Mats<T>, int64_t, int64_t, int);                 \
+  template void elimGather<T>(cudaStream_t, int, const DevElimPlan&, Mats<T>);                                          \
+  template void pseudoFactorSpans<T>(cudaStream_t, int, const DevSkel&, Mats<T>, int64_t, int64_t);                    \
+  template void assemble<T>(cudaStream_t, int, const DevSkel&, const int64_t*, Mats<T>, Work<T>, int64_t, int64_t,     \
+                            int64_t, int64_t, int64_t, int64_t, int64_t);                                               \
+  template void elimSolveL<T>(cudaStream_t, int, const DevSkel&, const DevElimPlan&, Mats<T>, Mats<T>, int64_t, int);  \
+  template void elimSolveLt<T>(cudaStream_t, int, const DevSkel&, const DevElimPlan&, Mats<T>, Mats<T>, int64_t, int); \
+  template void assembleVec<T>(cudaStream_t, int, const DevSkel&, Work<T>, int64_t, int64_t, int64_t, Mats<T>,         \
+                               int64_t, int);                                                                           \
+  template void assembleVecT<T>(cudaStream_t, int, const DevSkel&, Work<T>, int64_t, int64_t, int64_t, Mats<T>,        \
+                                int64_t, int);
+B200_INSTANTIATE_SPARSE(double)
+B200_INSTANTIATE_SPARSE(float)
+
+}  // namespace b200
+}  // namespace BaSpaCho

@@ -43,6 +43,8 @@ int guarded(F&& f) {
 
 struct SolverBox {
   SolverPtr solver;
+  void* stream = nullptr;     // cudaStream_t the device backend runs on (set_stream)
+  std::shared_ptr<void> ext;  // library-specific per-solver state (device staging buffers of *_host entry points)
 };
 
 struct PatternBox {
@@ -284,7 +286,11 @@ int CAPI(work_estimate)(const bspb200_solver* s, double* factor_flops, double* s
 }
 
 int CAPI(set_stream)(bspb200_solver* s, void* stream) {
-  return guarded([&] { reinterpret_cast<SolverBox*>(s)->solver->setStream(stream); });
+  return guarded([&] {
+    auto* box = reinterpret_cast<SolverBox*>(s);
+    box->solver->setStream(stream);
+    box->stream = stream;
+  });
 }
 
 int CAPI(set_fused)(bspb200_solver* s, int enabled) {

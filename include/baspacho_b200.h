@@ -112,6 +112,14 @@ int bspb200_do_elimination(bspb200_solver* s, int dtype, void* data, int range_i
 int bspb200_factor_solve_host(bspb200_solver* s, int dtype, const void* host_data, void* host_factor_out, void* host_vec,
                               int64_t ld, int n_rhs);
 
+/* ---- dense building blocks on DEVICE pointers (row-major), the kernels behind NumericCtx::potrf / trsm / saveSyrkGemm
+ * (reference MatOps.h:124-130); exposed for kernel-level parity tests and roofline measurements.
+ * C(m x n) = alpha * A(m x k) * B(n x k)^T + beta * C ; lower_only: only entries with col <= row are written */
+int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                        const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int lower_only, void* stream);
+/* in-place Cholesky of the (n + rows_below) x n trapezoid (top n x n = diagonal block, lower triangle), ld >= n */
+int bspb200_dev_potrf(int dtype, int64_t n, int64_t rows_below, void* A, int64_t ld, void* stream);
+
 /* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
 int64_t bspb200_launch_count(void);
 
