@@ -29,7 +29,7 @@ DECLARED_SYMBOLS = [
     "last_error", "version", "create_solver", "create_solver_from_skel", "destroy_solver", "solver_query",
     "solver_array", "densify", "damp", "block_offset", "work_estimate", "set_stream", "set_fused", "factor",
     "factor_batched", "solve", "solve_batched", "add_mv_from", "pseudo_factor_from", "do_elimination",
-    "factor_solve_host", "dev_gemm_nt", "dev_potrf", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
+    "factor_solve_host", "dev_gemm_nt", "dev_potrf", "profile_enable", "profile_report", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
     "pattern_free", "random_data", "fill_reducing_permutation",
 ]
 
@@ -76,6 +76,8 @@ class CApi:
         if prefix == "bspb200_":
             f("dev_gemm_nt", C.c_int, [C.c_int, c_i64, c_i64, c_i64, C.c_double, vp, c_i64, vp, c_i64, C.c_double, vp, c_i64, C.c_int, vp])
             f("dev_potrf", C.c_int, [C.c_int, c_i64, c_i64, vp, c_i64, vp])
+            f("profile_enable", C.c_int, [C.c_int])
+            f("profile_report", c_i64, [C.c_char_p, c_i64])
         f("launch_count", c_i64, [])
         f("gen_pattern", C.c_int, [C.c_int, c_dblp, C.c_int, c_i64, c_i64, c_i64, C.POINTER(vp)])
         f("pattern_order", c_i64, [vp])
@@ -90,6 +92,16 @@ class CApi:
         fn.restype = restype
         fn.argtypes = argtypes
         setattr(self, name, fn)
+
+    def profile(self, on):
+        self.check(self.profile_enable(int(on)))
+
+    def profile_json(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        if self.profile_report(buf, len(buf)) < 0:
+            raise BaspachoError(self.last_error().decode())
+        return json.loads(buf.value.decode())
 
     def check(self, rc):
         if rc != 0:

@@ -31,6 +31,37 @@ namespace b200 {
 std::atomic<int64_t>& launchCounter();
 inline void countLaunch(int64_t n = 1) { launchCounter().fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-kernel-class profiling (bench.py roofline): CUDA events around every launch of a class on the
+// launching stream, with the ALGORITHMIC flops / bytes of that launch accumulated beside the measured time.
+enum KernelClass {
+  KC_GEMM = 0,      // DMMA / SIMT GEMM-SYRK tiles (tensor/FMA bound)
+  KC_POTRF_BLOCK,   // one-CTA diagonal block Cholesky (latency bound)
+  KC_TRSM_BLOCK,    // panel triangular solve
+  KC_ELIM_FACTOR,   // sparse elimination step 1 (HBM bound)
+  KC_ELIM_GATHER,   // sparse elimination step 2 (HBM/L2 bound)
+  KC_ASSEMBLE,      // scatter-subtract into target lumps
+  KC_SOLVE_ELIM,    // elimination-range triangular solves (HBM bound)
+  KC_SOLVE_DENSE,   // dense-lump triangular solves / gemv (HBM bound)
+  KC_OTHER,
+  KC_COUNT
+};
+void profileEnable(bool on);
+bool profileEnabled();
+void profileBegin(cudaStream_t st, int cls, double flops, double bytes);
+void profileEnd(cudaStream_t st);
+std::string profileReportJson();  // synchronizes, aggregates and clears the recorded launches
+
+struct ProfScope {
+  ProfScope(cudaStream_t st, int cls, double flops, double bytes) : st_(st), on_(profileEnabled()) {
+    if (on_) profileBegin(st_, cls, flops, bytes);
+  }
+  ~ProfScope() {
+    if (on_) profileEnd(st_);
+  }
+  cudaStream_t st_;
+  bool on_;
+};
+
 #define B200_LAUNCH_CHECK()                 \
   do {                                      \
     ::BaSpaCho::b200::countLaunch();        \

@@ -96,7 +96,9 @@ struct B200SymbolicCtx : SymbolicCtx {
     DevElimPlan& d = e->dev;
     d.lumpsBegin = lumpsBegin, d.lumpsEnd = lumpsEnd, d.spanRowBegin = p.spanRowBegin;
     d.uniformLumpSize = p.uniformLumpSize;
+    d.factorEntries = p.factorEntries, d.gatherFlops = p.gatherFlops, d.gatherBytes = p.gatherEntries;
     d.numDst = p.numDst(), d.maxDstElems = p.maxDstElems;
+    d.uniRows = p.uniRows, d.uniCols = p.uniCols, d.uniK = p.uniK;
     d.dstOff = e->dstOff.ptr(), d.dstStride = e->dstStride.ptr(), d.dstRows = e->dstRows.ptr();
     d.dstCols = e->dstCols.ptr(), d.dstTaskPtr = e->dstTaskPtr.ptr(), d.taskA = e->taskA.ptr();
     d.taskB = e->taskB.ptr(), d.taskK = e->taskK.ptr();
@@ -109,6 +111,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     for (auto* v : {&p.dstRows, &p.dstCols, &p.rowChainK}) vector<int16_t>().swap(*v);
     for (auto* v : {&p.taskA, &p.taskB}) vector<uint32_t>().swap(*v);
     vector<uint16_t>().swap(p.taskK);
+    elimRegistry.push_back(e.get());  // owned by the Solver, which outlives every numeric/solve context
     return SymElimCtxPtr(e.release());
   }
 
@@ -126,6 +129,7 @@ struct B200SymbolicCtx : SymbolicCtx {
 
   const CoalescedBlockMatrixSkel& skel;
   cudaStream_t stream = nullptr;
+  vector<const B200SymElimCtx*> elimRegistry;  // elimination ranges in the order the Solver prepared them
   DevSkel dsk;
   DevBuf<int64_t> dSpanStart, dSpanToLump, dLumpStart, dLumpToSpan, dSpanOffsetInLump, dChainColPtr, dChainRowSpan,
       dChainData, dChainRowsTillEnd, dBoardColPtr, dBoardRowLump, dBoardChainColOrd, dPermutation;
@@ -195,7 +199,8 @@ struct B200NumericCtx : NumericCtx<TT> {
     BASPACHO_CHECK_EQ(elim->dev.lumpsEnd, lumpsEnd);
     auto timer = elim->elimStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream);
-    elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, lumpsBegin, lumpsEnd, elim->dev.uniformLumpSize);
+    elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, lumpsBegin, lumpsEnd, elim->dev.uniformLumpSize,
+                       2.0 * elim->dev.factorEntries * sizeof(T));
     elimGather<T>(sym.stream, m.batch, elim->dev, m);
   }
 
@@ -237,6 +242,52 @@ struct B200NumericCtx : NumericCtx<TT> {
                       srcColDataOffset, srcRectWidth, numBlockRows, numBlockCols, numRows);
   }
 
+  // ---- whole-range factorization in one backend call (MatOps.h addition; same work as Solver::internalFactorRange
+  // sequences through the fine-grained ops, reference Solver.cpp:164-219): sparse elimination of the ranges, then per
+  // dense lump the contributions of the already factored sources and ONE blocked factorization of the whole lump
+  // column (diagonal block + rows below) instead of separate potrf / trsm calls.
+  bool hasFusedFactor() override { return true; }
+
+  void fusedFactorRange(TT* data, int64_t startLump, int64_t upToLump) override {
+    Mats<T> m = mats.get(data, sym.stream);
+    int64_t denseFrom = 0;
+    for (const B200SymElimCtx* e : sym.elimRegistry) {
+      denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
+      if (e->dev.lumpsEnd > upToLump) return;
+      if (startLump > e->dev.lumpsBegin) continue;
+      elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, e->dev.lumpsBegin, e->dev.lumpsEnd, e->dev.uniformLumpSize,
+                         2.0 * e->dev.factorEntries * sizeof(T));
+      elimGather<T>(sym.stream, m.batch, e->dev, m);
+    }
+    const int64_t firstSrc = std::max(startLump, denseFrom);
+    for (int64_t l = firstSrc; l < skel.numLumps(); l++) {
+      bool prepared = false;
+      for (int64_t r = skel.boardRowPtr[l], rEnd = skel.boardRowPtr[l + 1] - 1; r < rEnd; r++) {
+        const int64_t src = skel.boardColLump[r];
+        if (src >= upToLump) break;
+        if (src < firstSrc) continue;
+        if (!prepared) prepareAssemble(l), prepared = true;
+        const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
+        const int64_t k = skel.lumpSize(src);
+        const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
+        const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
+        const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
+        const int64_t rowsInBoard = skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin;
+        const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
+        BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
+        Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
+        gemmNT<T>(sym.stream, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(temp(), 0), rowsInBoard,
+                  false);
+        b200::assemble<T>(sym.stream, m.batch, sym.dsk, sym.spanToChainOffset.ptr(), m, temp(), rowBegin,
+                          skel.lumpSize(l), cb + ch0, rowsInBoard, chEnd - ch0, ch1 - ch0, rowsToEnd);
+      }
+      if (l < upToLump) {
+        const int64_t n = skel.lumpSize(l);
+        potrfTrapezoid<T>(sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
+      }
+    }
+  }
+
   B200SymbolicCtx& sym;
   const CoalescedBlockMatrixSkel& skel;
   int64_t tempSize;
@@ -252,12 +303,15 @@ struct B200SolveCtx : SolveCtx<TT> {
     tlsSyncStream = sym.stream;
   }
 
-  Work<T> temp() {
+  // two scratch vectors of order x nRHS per batch item: [0] the gemv/assembleVec temp of the reference's solve ctx,
+  // [1] the solved-block staging of the blocked dense triangular solve
+  Work<T> temp(int which = 0) {
     Work<T> w;
     w.stride = std::max<int64_t>(1, skel.order() * nRHS);
-    w.base = (T*)sym.scratch((size_t)w.stride * batch * sizeof(T));
+    w.base = (T*)sym.scratch((size_t)w.stride * batch * sizeof(T) * 2) + (size_t)which * w.stride * batch;
     return w;
   }
+  Work<T> temp2() { return temp(1); }
 
   void sparseElimSolveL(const SymElimCtx& elimData, const TT* data, int64_t lumpsBegin, int64_t lumpsEnd, TT* C,
                         int64_t ldc) override {
@@ -291,13 +345,13 @@ struct B200SolveCtx : SolveCtx<TT> {
   void solveL(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0));
   }
 
   void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLtStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0));
   }
 
   void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,

@@ -16,8 +16,11 @@ ElimPlan buildElimPlan(const CoalescedBlockMatrixSkel& sk, int64_t lumpsBegin, i
     throw std::runtime_error("B200 sparse elimination plan: factor data beyond 2^32 entries is not supported yet");
 
   p.uniformLumpSize = lumpsEnd > lumpsBegin ? (int)sk.lumpSize(lumpsBegin) : 0;
-  for (int64_t l = lumpsBegin; l < lumpsEnd; l++)
+  for (int64_t l = lumpsBegin; l < lumpsEnd; l++) {
     if (sk.lumpSize(l) != p.uniformLumpSize) p.uniformLumpSize = 0;
+    p.factorEntries += (double)sk.lumpSize(l) * sk.lumpTotalRows(l);
+    p.gatherEntries += (double)sk.lumpSize(l) * (sk.lumpTotalRows(l) - sk.lumpSize(l));
+  }
 
   // ---- row view: per row span, the chains of the range's lumps found there (ascending source lump)
   auto firstBelow = [&](int64_t l) { return sk.chainColPtr[l] + (sk.lumpToSpan[l + 1] - sk.lumpToSpan[l]); };
@@ -80,6 +83,7 @@ ElimPlan buildElimPlan(const CoalescedBlockMatrixSkel& sk, int64_t lumpsBegin, i
       p.dstRows.push_back((int16_t)rowsB);
       p.dstCols.push_back((int16_t)rowsA);
       p.maxDstElems = std::max<int>(p.maxDstElems, (int)(rowsA * rowsB));
+      p.gatherEntries += 2.0 * rowsA * rowsB;
       pos[bRel] = (int32_t)run;
       run += perB[bRel];
       p.dstTaskPtr.push_back((int32_t)run);
@@ -95,10 +99,18 @@ ElimPlan buildElimPlan(const CoalescedBlockMatrixSkel& sk, int64_t lumpsBegin, i
         p.taskA[idx] = (uint32_t)sk.chainData[ca];
         p.taskB[idx] = (uint32_t)sk.chainData[cb];
         p.taskK[idx] = (uint16_t)sk.lumpSize(l);
+        p.gatherFlops += 2.0 * rowsA * (double)(sk.spanStart[sk.chainRowSpan[cb] + 1] - sk.spanStart[sk.chainRowSpan[cb]]) * sk.lumpSize(l);
       }
     }
     for (int64_t bRel : touched) perB[bRel] = 0;
     if (run >= (int64_t(1) << 31)) throw std::runtime_error("B200 sparse elimination plan: too many block pairs");
+  }
+  if (p.numDst() > 0) {
+    p.uniRows = p.dstRows[0], p.uniCols = p.dstCols[0], p.uniK = p.taskK.empty() ? 0 : p.taskK[0];
+    for (int64_t d = 0; d < p.numDst(); d++)
+      if (p.dstRows[d] != p.uniRows || p.dstCols[d] != p.uniCols) p.uniRows = p.uniCols = 0;
+    for (uint16_t k : p.taskK)
+      if (k != p.uniK) p.uniK = 0;
   }
   return p;
 }

@@ -30,6 +30,7 @@ struct ElimPlan {
   std::vector<uint32_t> taskB;      // offset of the B chain (rows = dstRows, cols = k)
   std::vector<uint16_t> taskK;      // width of the source lump
   int maxDstElems = 0;
+  int uniRows = 0, uniCols = 0, uniK = 0;  // > 0 when every destination / task has these dimensions
 
   // row view for the triangular solves: per row span >= spanRowBegin, the chains found in that row
   std::vector<int32_t> rowPtr;        // per row span - spanRowBegin (+1)
@@ -37,6 +38,9 @@ struct ElimPlan {
   std::vector<int32_t> rowChainCol;   // first scalar column of the source lump (lumpStart)
   std::vector<int16_t> rowChainK;     // width of the source lump
   int maxRowSpanSize = 0;
+
+  // algorithmic work (entries / flops), for the roofline report
+  double factorEntries = 0, gatherFlops = 0, gatherEntries = 0;
 
   int64_t numTasks() const { return (int64_t)taskA.size(); }
   int64_t numDst() const { return (int64_t)dstOff.size(); }

@@ -28,8 +28,12 @@ struct DevSkel {
 struct DevElimPlan {
   int64_t lumpsBegin, lumpsEnd, spanRowBegin;
   int uniformLumpSize;
+  double factorEntries;  // entries of the eliminated columns (s^2 + s*r summed): algorithmic traffic = 2x (step 1), 1x (solve)
+  double gatherFlops;    // 2 * sum over pair tasks of rowsA * rowsB * k
+  double gatherBytes;    // ENTRIES moved algorithmically by step 2: every below-diagonal source block once + 2x targets
   int64_t numDst;
   int maxDstElems;
+  int uniRows, uniCols, uniK;
   const int64_t* dstOff;
   const int32_t* dstStride;
   const int16_t* dstRows;
@@ -49,7 +53,7 @@ struct DevElimPlan {
 // step 1 of the sparse elimination: per lump, Cholesky of the diagonal block + X L^T = B on the rows below
 template <typename T>
 void elimFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t lumpsBegin, int64_t lumpsEnd,
-                     int uniformLumpSize);
+                     int uniformLumpSize, double profBytes = 0);
 // step 2: destination-major gather of the block-pair products
 template <typename T>
 void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> data);

@@ -219,87 +219,215 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(GemmShape s, T alpha,
   }
 }
 
-// ------------------------------------------------------------------------------------------------ one-CTA Cholesky
-// Right-looking, column by column, whole block resident in shared memory (odd row stride).
+// ------------------------------------------------------------------------------------------------ panel kernel
+// Diagonal block (n <= kNB) + the rows below it, in ONE launch:
+//   DO_POTRF: every CTA loads the n x n diagonal block and factors it (redundantly: the other SMs would idle anyway,
+//   and it removes a dependent launch + a reload of L); CTA 0 writes the factor back.
+//   Then CTA b solves X L^T = B for rows [R b, R b + R), R = 128 / G: G adjacent lanes share one row, each owns
+//   32/G columns of the current 32-column chunk in registers; L is read from shared memory as broadcast vector loads.
+// Cholesky phase: register resident, right looking. Thread (warp w, lane l) owns the entries (i, c) with
+//   i = l + 32 a (a < 3), c = w + 4 u (u < 24). Per column its owner warp publishes it (unscaled) to a double-buffered
+//   shared column, ONE barrier, then every thread updates its own registers with 1/pivot folded into the row operand.
+//   The column loop is unrolled over u so that every register index is static.
+constexpr int kNB = 96;          // max diagonal block
+constexpr int kLDS = 100;        // smem row stride of the block: rows 16-byte aligned for the vector loads (fp32 and fp64)
+constexpr int kPanelThreads = 128;
+constexpr int kLDX = 97;         // smem row stride of the row slab: odd (per-row walks are conflict free)
+
 template <typename T>
-__global__ void __launch_bounds__(512) potrf_block_kernel(int n, Operand<T> Aop, int64_t lda) {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  T* S = reinterpret_cast<T*>(smemRaw);
-  const int lds = n | 1;
-  T* __restrict__ A = Aop.at(blockIdx.z);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < n * n; i += nt) {
-    int r = i / n, c = i - r * n;
-    S[r * lds + c] = (c <= r) ? A[(int64_t)r * lda + c] : T(0);
-  }
-  __syncthreads();
-  for (int j = 0; j < n; j++) {
-    const T d = sqrt(S[j * lds + j]);
-    const T inv = T(1) / d;
-    __syncthreads();  // everyone has read the pivot before it is overwritten
-    for (int i = j + 1 + tid; i < n; i += nt) S[i * lds + j] *= inv;
-    if (tid == 0) S[j * lds + j] = d;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, cols j < c <= i
-    const int m = n - j - 1;
-    for (int e = tid; e < m * m; e += nt) {
-      int ri = e / m, ci = e - ri * m;
-      if (ci > ri) continue;
-      int i = j + 1 + ri, c = j + 1 + ci;
-      S[i * lds + c] -= S[i * lds + j] * S[c * lds + j];
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < n * n; i += nt) {
-    int r = i / n, c = i - r * n;
-    if (c <= r) A[(int64_t)r * lda + c] = S[r * lds + c];
-  }
+struct Vec4 {
+  T v[4];
+};
+__device__ __forceinline__ Vec4<double> load4(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  return {{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ Vec4<float> load4(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  return {{a.x, a.y, a.z, a.w}};
 }
 
-// ------------------------------------------------------------------------------------------------ X L^T = B, L <= block
-// CTA = ROWS rows of B (one thread per row, row kept in shared memory with odd stride), L packed lower in smem.
-template <typename T, int ROWS>
-__global__ void __launch_bounds__(ROWS) trsm_block_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
-                                                          Operand<T> Bop, int64_t ldb) {
+template <typename T, bool DO_POTRF, int G>
+__global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
+                                                             Operand<T> Bop, int64_t ldb) {
+  constexpr int NW = kPanelThreads / 32;  // 4 warps
+  constexpr int R = kPanelThreads / G;    // rows per CTA
+  constexpr int W = 32 / G;               // columns of a chunk per thread
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  T* Ls = reinterpret_cast<T*>(smemRaw);  // packed lower: (j, q) -> j(j+1)/2 + q
-  const int ldx = n | 1;
-  T* Xs = Ls + (n * (n + 1) / 2 + 1);
-  const T* __restrict__ L = Lop.at(blockIdx.z);
-  T* __restrict__ B = Bop.at(blockIdx.z);
-  const int tid = threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS;
-  const int nr = (int)min((int64_t)ROWS, rows - r0);
-  for (int i = tid; i < n * n; i += ROWS) {
-    int r = i / n, c = i - r * n;
-    if (c <= r) Ls[r * (r + 1) / 2 + c] = L[(int64_t)r * ldl + c];
-  }
-  for (int i = tid; i < nr * n; i += ROWS) {
-    int r = i / n, c = i - r * n;
-    Xs[r * ldx + c] = B[(r0 + r) * ldb + c];
+  T* S = reinterpret_cast<T*>(smemRaw);  // [kNB][kLDS], zero padded
+  T* invd = S + kNB * kLDS;              // [kNB]
+  T* Xs = invd + kNB;                    // [R][kLDX]  (also the 2 x kNB column buffer of the Cholesky phase)
+  T* __restrict__ L = Lop.at(blockIdx.z);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < kNB * kLDS + kNB; i += kPanelThreads) S[i] = T(0);
+  __syncthreads();
+  {  // lower triangle -> smem, all loads in flight at once
+    T tmp[(kNB / NW) * (kNB / 32)];
+#pragma unroll
+    for (int a = 0; a < kNB / NW; a++)
+#pragma unroll
+      for (int u = 0; u < kNB / 32; u++) {
+        const int r = warp + NW * a, c = lane + 32 * u;
+        tmp[a * (kNB / 32) + u] = (c <= r && r < n) ? L[(int64_t)r * ldl + c] : T(0);
+      }
+#pragma unroll
+    for (int a = 0; a < kNB / NW; a++)
+#pragma unroll
+      for (int u = 0; u < kNB / 32; u++) {
+        const int r = warp + NW * a, c = lane + 32 * u;
+        if (c <= r && r < n) S[r * kLDS + c] = tmp[a * (kNB / 32) + u];
+      }
   }
   __syncthreads();
-  if (tid < nr) {
-    T* x = Xs + tid * ldx;
-    for (int j = 0; j < n; j++) {
-      const T* lj = Ls + j * (j + 1) / 2;
-      T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      int q = 0;
-      for (; q + 4 <= j; q += 4) {
-        s0 += x[q] * lj[q];
-        s1 += x[q + 1] * lj[q + 1];
-        s2 += x[q + 2] * lj[q + 2];
-        s3 += x[q + 3] * lj[q + 3];
+
+  if (DO_POTRF) {
+    constexpr int RA = kNB / 32, CU = kNB / NW;  // 3 row slots, 24 column slots
+    T* colbuf = Xs;
+    T reg[RA][CU];
+#pragma unroll
+    for (int a = 0; a < RA; a++)
+#pragma unroll
+      for (int u = 0; u < CU; u++) reg[a][u] = S[(lane + 32 * a) * kLDS + warp + NW * u];
+#pragma unroll
+    for (int u = 0; u < CU; u++) {
+      for (int w = 0; w < NW; w++) {
+        const int j = NW * u + w;
+        if (j >= n) break;
+        T* cb = colbuf + (j & 1) * kNB;
+        if (warp == w) {
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (lane + 32 * a >= j) cb[lane + 32 * a] = reg[a][u];
+        }
+        __syncthreads();
+        const T piv = cb[j];
+        const T rs = rsqrt(piv);
+        const T invp = rs * rs;
+        T li[RA];
+#pragma unroll
+        for (int a = 0; a < RA; a++) li[a] = (lane + 32 * a > j) ? cb[lane + 32 * a] * invp : T(0);
+#pragma unroll
+        for (int u2 = u; u2 < CU; u2++) {
+          const int c = warp + NW * u2;
+          if (c > j) {  // warp uniform
+            const T sc = cb[c];
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (c <= lane + 32 * a) reg[a][u2] -= li[a] * sc;
+          }
+        }
+        if (warp == w) {
+#pragma unroll
+          for (int a = 0; a < RA; a++) {
+            const int i = lane + 32 * a;
+            if (i == j) reg[a][u] = piv * rs;
+            else if (i > j) reg[a][u] *= rs;
+          }
+        }
       }
-      for (; q < j; q++) s0 += x[q] * lj[q];
-      x[j] = (x[j] - ((s0 + s1) + (s2 + s3))) / lj[j];
+    }
+    __syncthreads();  // the column buffers are no longer read
+#pragma unroll
+    for (int a = 0; a < RA; a++)
+#pragma unroll
+      for (int u = 0; u < CU; u++) {
+        const int i = lane + 32 * a, c = warp + NW * u;
+        if (c <= i && i < n) S[i * kLDS + c] = reg[a][u];
+      }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+#pragma unroll
+      for (int a = 0; a < kNB / NW; a++)
+#pragma unroll
+        for (int u = 0; u < kNB / 32; u++) {
+          const int r = warp + NW * a, c = lane + 32 * u;
+          if (c <= r && r < n) L[(int64_t)r * ldl + c] = S[r * kLDS + c];
+        }
+    }
+  }
+  if (rows <= 0) return;
+  if (tid < n) invd[tid] = T(1) / S[tid * kLDS + tid];
+
+  T* __restrict__ B = Bop.at(blockIdx.z);
+  const int64_t r0 = (int64_t)blockIdx.x * R;
+  const int nr = (int)min((int64_t)R, rows - r0);
+  for (int r = warp; r < nr; r += NW)
+#pragma unroll
+    for (int u = 0; u < kNB / 32; u++) {
+      const int c = lane + 32 * u;
+      if (c < n) Xs[r * kLDX + c] = B[(r0 + r) * ldb + c];
+    }
+  __syncthreads();
+  {
+    const int row = tid / G, g = tid % G;  // G adjacent lanes share a row
+    const bool live = row < nr;
+    T* x = Xs + (live ? row : 0) * kLDX;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      const int cg = c0 + g * W;  // first column of this thread's piece
+      T acc[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) acc[k] = (cg + k < n) ? x[cg + k] : T(0);
+      for (int q0 = 0; q0 < c0; q0 += 4) {
+        const T x0 = x[q0], x1 = x[q0 + 1], x2 = x[q0 + 2], x3 = x[q0 + 3];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+          const Vec4<T> l = load4(S + (cg + k) * kLDS + q0);
+          acc[k] -= x0 * l.v[0];
+          acc[k] -= x1 * l.v[1];
+          acc[k] -= x2 * l.v[2];
+          acc[k] -= x3 * l.v[3];
+        }
+      }
+      // triangular part of the chunk, piece by piece: piece p is finished by its owner lane, broadcast with shuffles
+      // to the lanes of the same row that own later pieces
+#pragma unroll
+      for (int p = 0; p < G; p++) {
+        if (g == p) {
+#pragma unroll
+          for (int k = 0; k < W; k++) {
+            acc[k] *= invd[cg + k];
+#pragma unroll
+            for (int k2 = k + 1; k2 < W; k2++) acc[k2] -= acc[k] * S[(cg + k2) * kLDS + cg + k];
+          }
+        }
+        if (p + 1 < G) {
+#pragma unroll
+          for (int m = 0; m < W; m++) {
+            const T xp = __shfl_sync(0xffffffffu, acc[m], (lane / G) * G + p);
+            if (g > p) {
+#pragma unroll
+              for (int k = 0; k < W; k++) acc[k] -= xp * S[(cg + k) * kLDS + c0 + p * W + m];
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < W; k++)
+          if (cg + k < n) x[cg + k] = acc[k];
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
-  for (int i = tid; i < nr * n; i += ROWS) {
-    int r = i / n, c = i - r * n;
-    B[(r0 + r) * ldb + c] = Xs[r * ldx + c];
+  for (int r = warp; r < nr; r += NW)
+#pragma unroll
+    for (int u = 0; u < kNB / 32; u++) {
+      const int c = lane + 32 * u;
+      if (c < n) B[(r0 + r) * ldb + c] = Xs[r * kLDX + c];
+    }
+}
+
+// algorithmic flops of C = A B^T (lower-only: entries with col <= row)
+double gemmFlops(int64_t m, int64_t n, int64_t k, bool lowerOnly) {
+  double elems = (double)m * n;
+  if (lowerOnly) {
+    double nn = (double)std::min(m, n);
+    elems = nn * (nn + 1) / 2 + (double)std::max<int64_t>(0, m - n) * n;
   }
+  return 2.0 * elems * k;
 }
 
 template <typename KernelT>
@@ -336,12 +464,14 @@ void gemmNT<double>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k,
                     bool lowerOnly) {
   if (m <= 0 || n <= 0) return;
   GemmShape s{m, n, k, lda, ldb, ldc, lowerOnly ? 1 : 0};
+  ProfScope prof(st, KC_GEMM, gemmFlops(m, n, k, lowerOnly) * batch, 0);
   // 16-byte cp.async needs even element offsets/strides and 16B-aligned bases (cudaMalloc bases are; batch pointers
   // supplied by the caller are only guaranteed 8B aligned -> 8-byte copies there)
   bool aligned16 = !A.many && !B.many && (lda % 2 == 0) && (ldb % 2 == 0) && (A.off % 2 == 0) && (B.off % 2 == 0) &&
                    (A.bstride % 2 == 0) && (B.bstride % 2 == 0) && ((uintptr_t)A.base % 16 == 0) &&
                    ((uintptr_t)B.base % 16 == 0);
-  if (m >= 96 && n >= 96)
+  // big tiles when they fill the machine, small ones for skinny / small products
+  if (m >= 96 && n >= 96 && (int64_t)ceilDiv(m, 128) * ceilDiv(n, 128) * batch >= 96)
     launchGemmF64<128, 128, 16, 64, 32, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
   else
     launchGemmF64<64, 64, 16, 32, 16, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
@@ -353,6 +483,7 @@ void gemmNT<float>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k, 
                    bool lowerOnly) {
   if (m <= 0 || n <= 0) return;
   GemmShape s{m, n, k, lda, ldb, ldc, lowerOnly ? 1 : 0};
+  ProfScope prof(st, KC_GEMM, gemmFlops(m, n, k, lowerOnly) * batch, 0);
   dim3 grid(ceilDiv(n, 64), ceilDiv(m, 64), batch);
   gemm_nt_simt_kernel<float, 64, 64, 16><<<grid, 256, 0, st>>>(s, alpha, A, B, beta, C);
   B200_LAUNCH_CHECK();
@@ -360,35 +491,56 @@ void gemmNT<float>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k, 
 
 template <>
 int maxBlockDim<double>() {
-  return 96;
+  return kNB;
 }
 template <>
 int maxBlockDim<float>() {
-  return 128;
+  return kNB;
+}
+
+template <typename T, bool DO_POTRF, int G>
+static void launchPanelG(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
+                         int64_t ldb) {
+  constexpr int R = kPanelThreads / G;
+  size_t smem = ((size_t)kNB * kLDS + kNB + std::max<size_t>((size_t)R * kLDX, 2 * kNB)) * sizeof(T);
+  static bool once = (setSmem(panel_kernel<T, DO_POTRF, G>, smem), true);
+  (void)once;
+  int ctas = std::max(1, ceilDiv(rows, R));
+  panel_kernel<T, DO_POTRF, G><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T, bool DO_POTRF>
+static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
+                        int64_t ldb) {
+  if (n > kNB) throw std::runtime_error("panel kernel: block too large");
+  // rows per CTA: 32 (4 lanes per row) unless there are so many rows that 64 per CTA still fills the machine
+  if (rows * batch > 64 * 296)
+    launchPanelG<T, DO_POTRF, 2>(st, batch, n, rows, L, ldl, B, ldb);
+  else
+    launchPanelG<T, DO_POTRF, 4>(st, batch, n, rows, L, ldl, B, ldb);
 }
 
 template <typename T>
 void potrfBlock(cudaStream_t st, int batch, int n, Operand<T> A, int64_t lda) {
   if (n <= 0) return;
-  if (n > maxBlockDim<T>()) throw std::runtime_error("potrfBlock: block too large");
-  size_t smem = (size_t)n * (n | 1) * sizeof(T);
-  static bool once = (setSmem(potrf_block_kernel<T>, (size_t)maxBlockDim<T>() * (maxBlockDim<T>() | 1) * sizeof(T)), true);
-  (void)once;
-  int threads = n <= 16 ? 64 : n <= 32 ? 128 : n <= 64 ? 256 : 512;
-  potrf_block_kernel<T><<<dim3(1, 1, batch), threads, smem, st>>>(n, A, lda);
-  B200_LAUNCH_CHECK();
+  ProfScope prof(st, KC_POTRF_BLOCK, (double)n * n * n / 3 * batch, 0);
+  launchPanel<T, true>(st, batch, n, 0, A, lda, A, lda);
 }
 
 template <typename T>
 void trsmBlock(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B, int64_t ldb) {
   if (n <= 0 || rows <= 0) return;
-  if (n > maxBlockDim<T>()) throw std::runtime_error("trsmBlock: block too large");
-  constexpr int ROWS = 64;
-  auto smemFor = [](int nn) { return ((size_t)nn * (nn + 1) / 2 + 1 + (size_t)ROWS * (nn | 1)) * sizeof(T); };
-  static bool once = (setSmem(trsm_block_kernel<T, ROWS>, smemFor(maxBlockDim<T>())), true);
-  (void)once;
-  trsm_block_kernel<T, ROWS><<<dim3(ceilDiv(rows, ROWS), 1, batch), ROWS, smemFor(n), st>>>(n, rows, L, ldl, B, ldb);
-  B200_LAUNCH_CHECK();
+  ProfScope prof(st, KC_TRSM_BLOCK, (double)rows * n * n * batch, 0);
+  launchPanel<T, false>(st, batch, n, rows, L, ldl, B, ldb);
+}
+
+// diagonal block + rows below in one launch (leaf of the blocked factorization)
+template <typename T>
+static void potrfTrsmPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
+                           int64_t ldb) {
+  ProfScope prof(st, KC_POTRF_BLOCK, ((double)n * n * n / 3 + (double)rows * n * n) * batch, 0);
+  launchPanel<T, true>(st, batch, n, rows, L, ldl, B, ldb);
 }
 
 // Recursive blocked Cholesky of the (n + rowsBelow) x n trapezoid (row-major, ld). Columns [c0, c0 + w):
@@ -399,9 +551,7 @@ static void potrfRec(cudaStream_t st, int batch, int64_t totalRows, int64_t c0, 
   const int nb = maxBlockDim<T>();
   if (w <= nb) {
     Operand<T> diag = shifted(A, c0 * ld + c0);
-    potrfBlock<T>(st, batch, (int)w, diag, ld);
-    int64_t below = totalRows - (c0 + w);
-    if (below > 0) trsmBlock<T>(st, batch, (int)w, below, diag, ld, shifted(A, (c0 + w) * ld + c0), ld);
+    potrfTrsmPanel<T>(st, batch, (int)w, totalRows - (c0 + w), diag, ld, shifted(A, (c0 + w) * ld + c0), ld);
     return;
   }
   int64_t blocks = (w + nb - 1) / nb;  // >= 2

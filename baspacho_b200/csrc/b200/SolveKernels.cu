@@ -10,46 +10,75 @@ namespace {
 
 constexpr int kTrsvWarps = 4;
 
-// one CTA: L (n x n lower) in shared memory, one warp per right-hand side
+// one CTA: L (n x n lower, n <= 96) in shared memory (odd stride: row and column walks are both conflict free),
+// one warp per right-hand side with the vector in registers (3 entries per lane); the pivot entry is broadcast
+// with a shuffle, so a column step costs one shuffle + one multiply + up to 3 FMAs and no barrier.
+constexpr int kTB = 96, kTLD = 97;
 template <typename T>
 __global__ void __launch_bounds__(kTrsvWarps * 32) trsv_block_kernel(int n, Operand<T> Lop, int64_t ldl, Operand<T> Cop,
                                                                      int64_t ldc, int nRHS, bool transposed) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   T* Ls = reinterpret_cast<T*>(smemRaw);
-  const int lds = n | 1;
-  T* xs = Ls + n * lds;
+  T* invd = Ls + kTB * kTLD;
   const T* __restrict__ L = Lop.at(blockIdx.z);
   T* C = Cop.at(blockIdx.z);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n * n; i += blockDim.x) {
-    int r = i / n, c = i - r * n;
-    if (c <= r) Ls[r * lds + c] = L[(int64_t)r * ldl + c];
+  {
+    T tmp[(kTB / kTrsvWarps) * 3];
+#pragma unroll
+    for (int a = 0; a < kTB / kTrsvWarps; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + kTrsvWarps * a, c = lane + 32 * u;
+        tmp[a * 3 + u] = (c <= r && r < n) ? L[(int64_t)r * ldl + c] : T(0);
+      }
+#pragma unroll
+    for (int a = 0; a < kTB / kTrsvWarps; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + kTrsvWarps * a, c = lane + 32 * u;
+        if (c <= r && r < n) Ls[r * kTLD + c] = tmp[a * 3 + u];
+      }
   }
   __syncthreads();
-  T* x = xs + warp * n;
+  if (tid < n) invd[tid] = T(1) / Ls[tid * kTLD + tid];
+  __syncthreads();
   for (int rhs = warp; rhs < nRHS; rhs += kTrsvWarps) {
     T* c = C + (int64_t)rhs * ldc;
-    for (int i = lane; i < n; i += 32) x[i] = c[i];
-    __syncwarp();
+    T x[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) x[u] = (lane + 32 * u < n) ? c[lane + 32 * u] : T(0);
     if (!transposed) {
-      for (int j = 0; j < n; j++) {
-        const T xj = x[j] / Ls[j * lds + j];
-        __syncwarp();
-        if (lane == 0) x[j] = xj;
-        for (int i = j + 1 + lane; i < n; i += 32) x[i] -= Ls[i * lds + j] * xj;
-        __syncwarp();
-      }
+#pragma unroll
+      for (int uj = 0; uj < 3; uj++)
+        for (int jj = 0; jj < 32 && 32 * uj + jj < n; jj++) {
+          const int j = 32 * uj + jj;
+          const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+          if (lane == jj) x[uj] = xj;
+#pragma unroll
+          for (int u = uj; u < 3; u++) {
+            const int i = lane + 32 * u;
+            if (i > j && i < n) x[u] -= Ls[i * kTLD + j] * xj;
+          }
+        }
     } else {
-      for (int j = n - 1; j >= 0; j--) {
-        const T xj = x[j] / Ls[j * lds + j];
-        __syncwarp();
-        if (lane == 0) x[j] = xj;
-        for (int i = lane; i < j; i += 32) x[i] -= Ls[j * lds + i] * xj;
-        __syncwarp();
-      }
+#pragma unroll
+      for (int uj = 2; uj >= 0; uj--)
+        for (int jj = 31; jj >= 0; jj--) {
+          const int j = 32 * uj + jj;
+          if (j >= n) continue;
+          const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+          if (lane == jj) x[uj] = xj;
+#pragma unroll
+          for (int u = 0; u <= uj; u++) {
+            const int i = lane + 32 * u;
+            if (i < j) x[u] -= Ls[j * kTLD + i] * xj;
+          }
+        }
     }
-    for (int i = lane; i < n; i += 32) c[i] = x[i];
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+      if (lane + 32 * u < n) c[lane + 32 * u] = x[u];
   }
 }
 
@@ -149,7 +178,8 @@ __global__ void __launch_bounds__(128) symm_lower_kernel(int64_t n, T alpha, Ope
 template <typename T>
 void trsvBlock(cudaStream_t st, int batch, int n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
                bool transposed) {
-  auto smemFor = [](int nn) { return ((size_t)nn * (nn | 1) + (size_t)kTrsvWarps * nn) * sizeof(T); };
+  if (n > kTB) throw std::runtime_error("trsvBlock: block too large");
+  auto smemFor = [](int) { return ((size_t)kTB * kTLD + kTB) * sizeof(T); };
   static bool once = [&] {
     size_t mx = smemFor(maxBlockDim<T>());
     if (mx > 48 * 1024)
@@ -157,6 +187,7 @@ void trsvBlock(cudaStream_t st, int batch, int n, Operand<T> L, int64_t ldl, Ope
     return true;
   }();
   (void)once;
+  ProfScope prof(st, KC_SOLVE_DENSE, (double)n * n * nRHS * batch, (double)n * (n + 1) / 2 * sizeof(T) * batch);
   trsv_block_kernel<T><<<dim3(1, 1, batch), kTrsvWarps * 32, smemFor(n), st>>>(n, L, ldl, C, ldc, nRHS, transposed);
   B200_LAUNCH_CHECK();
 }
@@ -167,6 +198,7 @@ template <typename T>
 void gemvRows(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm, Operand<T> X,
               int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate) {
   if (rows <= 0 || nRHS <= 0) return;
+  ProfScope prof(st, KC_SOLVE_DENSE, 2.0 * rows * cols * nRHS * batch, (double)rows * cols * sizeof(T) * batch);
   if (cols <= 16)
     gemv_rows_thread_kernel<T><<<dim3(ceilDiv(rows, 256), 1, batch), 256, 0, st>>>(
         rows, cols, alpha, M, ldm, X, ldx, out, outRowStride, outColStride, nRHS, accumulate);
@@ -180,6 +212,7 @@ template <typename T>
 void gemvColsT(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm,
                Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS) {
   if (rows <= 0 || cols <= 0 || nRHS <= 0) return;
+  ProfScope prof(st, KC_SOLVE_DENSE, 2.0 * rows * cols * nRHS * batch, (double)rows * cols * sizeof(T) * batch);
   gemv_cols_t_kernel<T><<<dim3(ceilDiv(cols, 32), 1, batch), 256, 0, st>>>(rows, cols, alpha, M, ldm, in, inRowStride,
                                                                           inColStride, X, ldx, nRHS);
   B200_LAUNCH_CHECK();
@@ -193,28 +226,174 @@ void symmLower(cudaStream_t st, int batch, int64_t n, T alpha, Operand<T> M, Ope
   B200_LAUNCH_CHECK();
 }
 
+// One block step of the dense triangular solve in ONE launch: every CTA solves the diagonal block (redundantly, one
+// warp per right-hand side, vector in registers) and then applies its share of the update with the solved block:
+//   forward : y[row] -= L[row, block] . x_block      for 64 rows below the block per CTA (warp per row)
+//   backward: y[col] -= L[block, col]^T . x_block    for 128 columns before the block per CTA (thread per column)
+// The solved block goes to a scratch vector (the input block must stay intact for the other CTAs).
+constexpr int kStepRows = 64, kStepCols = 128;
+template <typename T, bool TR>
+__global__ void __launch_bounds__(kTrsvWarps * 32)
+    solve_step_kernel(int64_t n, int64_t j0, int jb, Operand<T> Lop, int64_t ldl, Operand<T> Cop, int64_t ldc,
+                      Operand<T> Xop, int64_t ldx, int nRHS) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* Ls = reinterpret_cast<T*>(smemRaw);
+  T* invd = Ls + kTB * kTLD;
+  T* xs = invd + kTB;  // [kTrsvWarps][kTB]
+  const T* __restrict__ L = Lop.at(blockIdx.z);
+  T* C = Cop.at(blockIdx.z);
+  T* X = Xop.at(blockIdx.z);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const T* D = L + j0 * ldl + j0;
+    T tmp[(kTB / kTrsvWarps) * 3];
+#pragma unroll
+    for (int a = 0; a < kTB / kTrsvWarps; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + kTrsvWarps * a, c = lane + 32 * u;
+        tmp[a * 3 + u] = (c <= r && r < jb) ? D[(int64_t)r * ldl + c] : T(0);
+      }
+#pragma unroll
+    for (int a = 0; a < kTB / kTrsvWarps; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + kTrsvWarps * a, c = lane + 32 * u;
+        if (c <= r && r < jb) Ls[r * kTLD + c] = tmp[a * 3 + u];
+      }
+  }
+  __syncthreads();
+  if (tid < jb) invd[tid] = T(1) / Ls[tid * kTLD + tid];
+  __syncthreads();
+  for (int g0 = 0; g0 < nRHS; g0 += kTrsvWarps) {
+    const int rhs = g0 + warp;
+    if (rhs < nRHS) {
+      const T* c = C + (int64_t)rhs * ldc + j0;
+      T x[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++) x[u] = (lane + 32 * u < jb) ? c[lane + 32 * u] : T(0);
+      if (!TR) {
+#pragma unroll
+        for (int uj = 0; uj < 3; uj++)
+          for (int jj = 0; jj < 32 && 32 * uj + jj < jb; jj++) {
+            const int j = 32 * uj + jj;
+            const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+            if (lane == jj) x[uj] = xj;
+#pragma unroll
+            for (int u = uj; u < 3; u++) {
+              const int i = lane + 32 * u;
+              if (i > j && i < jb) x[u] -= Ls[i * kTLD + j] * xj;
+            }
+          }
+      } else {
+#pragma unroll
+        for (int uj = 2; uj >= 0; uj--)
+          for (int jj = 31; jj >= 0; jj--) {
+            const int j = 32 * uj + jj;
+            if (j >= jb) continue;
+            const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+            if (lane == jj) x[uj] = xj;
+#pragma unroll
+            for (int u = 0; u <= uj; u++) {
+              const int i = lane + 32 * u;
+              if (i < j) x[u] -= Ls[j * kTLD + i] * xj;
+            }
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int i = lane + 32 * u;
+        xs[warp * kTB + i] = (i < jb) ? x[u] : T(0);
+        if (blockIdx.x == 0 && i < jb) X[(int64_t)rhs * ldx + j0 + i] = x[u];
+      }
+    }
+    __syncthreads();
+    const int ng = min(kTrsvWarps, nRHS - g0);
+    if (!TR) {
+      const int64_t rbeg = j0 + jb + (int64_t)blockIdx.x * kStepRows;
+      constexpr int RPW = kStepRows / kTrsvWarps;  // rows per warp
+#pragma unroll 4
+      for (int rr = 0; rr < RPW; rr++) {
+        const int64_t row = rbeg + warp * RPW + rr;
+        if (row >= n) break;
+        const T* m = L + row * ldl + j0;
+        T mv[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) mv[u] = (lane + 32 * u < jb) ? m[lane + 32 * u] : T(0);
+        for (int q = 0; q < ng; q++) {
+          T v = mv[0] * xs[q * kTB + lane] + mv[1] * xs[q * kTB + lane + 32] + mv[2] * xs[q * kTB + lane + 64];
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) C[(int64_t)(g0 + q) * ldc + row] -= v;
+        }
+      }
+    } else {
+      const int64_t col = (int64_t)blockIdx.x * kStepCols + tid;
+      if (col < j0) {
+        T acc[kTrsvWarps];
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++) acc[q] = T(0);
+        const T* m = L + j0 * ldl + col;
+#pragma unroll 8
+        for (int r = 0; r < jb; r++) {
+          const T mv = m[(int64_t)r * ldl];
+#pragma unroll
+          for (int q = 0; q < kTrsvWarps; q++) acc[q] += mv * xs[q * kTB + r];
+        }
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++)
+          if (q < ng) C[(int64_t)(g0 + q) * ldc + col] -= acc[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void copy_vec_kernel(int64_t n, int nRHS, Operand<T> Xop, int64_t ldx, Operand<T> Cop, int64_t ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * nRHS) return;
+  const int64_t r = i % n, c = i / n;
+  Cop.at(blockIdx.z)[c * ldc + r] = Xop.at(blockIdx.z)[c * ldx + r];
+}
+
 template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
-             bool transposed) {
+             bool transposed, Operand<T> scratch) {
   if (n <= 0 || nRHS <= 0) return;
-  const int nb = maxBlockDim<T>();
+  const int nb = kTB;
+  if (n <= nb) {  // a single block: solved in place
+    trsvBlock<T>(st, batch, (int)n, L, ldl, C, ldc, nRHS, transposed);
+    return;
+  }
+  const size_t smem = ((size_t)kTB * kTLD + kTB + (size_t)kTrsvWarps * kTB) * sizeof(T);
+  static bool once = [&] {
+    B200_CUDA(cudaFuncSetAttribute(solve_step_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(solve_step_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return true;
+  }();
+  (void)once;
+  const int64_t ldx = n;
   if (!transposed) {
     for (int64_t j0 = 0; j0 < n; j0 += nb) {
       int64_t jb = std::min<int64_t>(nb, n - j0), rb = n - j0 - jb;
-      trsvBlock<T>(st, batch, (int)jb, shifted(L, j0 * ldl + j0), ldl, shifted(C, j0), ldc, nRHS, false);
-      if (rb > 0)  // x[below] -= L[below, block] * x[block]
-        gemvRows<T>(st, batch, rb, jb, T(-1), shifted(L, (j0 + jb) * ldl + j0), ldl, shifted(C, j0), ldc,
-                    shifted(C, j0 + jb), 1, ldc, nRHS, true);
+      ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * rb * jb) * nRHS * batch,
+                     (double)(jb * (jb + 1) / 2 + rb * jb) * sizeof(T) * batch);
+      solve_step_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kTrsvWarps * 32, smem, st>>>(
+          n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS);
+      B200_LAUNCH_CHECK();
     }
   } else {
-    int64_t j0 = ((n - 1) / nb) * nb;
-    for (; j0 >= 0; j0 -= nb) {
+    for (int64_t j0 = ((n - 1) / nb) * nb; j0 >= 0; j0 -= nb) {
       int64_t jb = std::min<int64_t>(nb, n - j0);
-      trsvBlock<T>(st, batch, (int)jb, shifted(L, j0 * ldl + j0), ldl, shifted(C, j0), ldc, nRHS, true);
-      if (j0 > 0)  // x[before] -= L[block, before]^T * x[block]
-        gemvColsT<T>(st, batch, jb, j0, T(-1), shifted(L, j0 * ldl), ldl, shifted(C, j0), 1, ldc, C, ldc, nRHS);
+      ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * j0 * jb) * nRHS * batch,
+                     (double)(jb * (jb + 1) / 2 + j0 * jb) * sizeof(T) * batch);
+      solve_step_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kTrsvWarps * 32, smem, st>>>(
+          n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS);
+      B200_LAUNCH_CHECK();
     }
   }
+  copy_vec_kernel<T><<<dim3(ceilDiv(n * nRHS, 256), 1, batch), 256, 0, st>>>(n, nRHS, scratch, ldx, C, ldc);
+  B200_LAUNCH_CHECK();
 }
 
 #define B200_INSTANTIATE_SOLVE(T)                                                                                       \
@@ -223,7 +402,7 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   template void gemvColsT<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t, int64_t, \
                              Operand<T>, int64_t, int);                                                                 \
   template void symmLower<T>(cudaStream_t, int, int64_t, T, Operand<T>, Operand<T>, int64_t, Operand<T>, int64_t, int); \
-  template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool);
+  template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>);
 B200_INSTANTIATE_SOLVE(double)
 B200_INSTANTIATE_SOLVE(float)
 

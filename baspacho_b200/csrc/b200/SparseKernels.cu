@@ -107,6 +107,51 @@ __global__ void __launch_bounds__(256) elim_gather_kernel(DevElimPlan p, Mats<T>
   }
 }
 
+// Fixed-shape variant (every destination NR x NC, every source lump K wide - e.g. 6x6 camera blocks fed by 3-wide
+// points): LANES consecutive lanes own one destination and split its pair tasks; a lane keeps the whole NR x NC
+// partial product in registers (each block is read once, 8-byte loads of consecutive addresses per lane), then a
+// fixed-order butterfly over the LANES lanes and one read-modify-write of the target per entry.
+template <typename T, int NR, int NC, int K, int LANES>
+__global__ void __launch_bounds__(128) elim_gather_fixed_kernel(DevElimPlan p, Mats<T> mats) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t d = gid / LANES;
+  const int sub = (int)(gid % LANES);
+  const bool live = d < p.numDst;
+  T* data = mats.at(blockIdx.z);
+  T acc[NR * NC];
+#pragma unroll
+  for (int e = 0; e < NR * NC; e++) acc[e] = T(0);
+  if (live) {
+    const int tEnd = p.dstTaskPtr[d + 1];
+    for (int t = p.dstTaskPtr[d] + sub; t < tEnd; t += LANES) {
+      const T* __restrict__ a = data + p.taskA[t];
+      const T* __restrict__ b = data + p.taskB[t];
+      T av[NC * K], bv[NR * K];
+#pragma unroll
+      for (int i = 0; i < NC * K; i++) av[i] = a[i];
+#pragma unroll
+      for (int i = 0; i < NR * K; i++) bv[i] = b[i];
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int q = 0; q < K; q++) acc[r * NC + c] += bv[r * K + q] * av[c * K + q];
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1)
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  if (live) {
+    T* dst = data + p.dstOff[d];
+    const int64_t stride = p.dstStride[d];
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++)
+      if (e % LANES == sub) dst[(e / NC) * stride + (e % NC)] -= acc[e];
+  }
+}
+
 // one CTA (one warp) per span: diagonal block of the span + the rows below it, columns of this span only
 // (reference factor_spans_kernel, MatOpsCuda.cu:188-233)
 template <typename T>
@@ -295,8 +340,9 @@ void launchFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> da
 
 template <typename T>
 void elimFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t lumpsBegin, int64_t lumpsEnd,
-                     int uniformLumpSize) {
+                     int uniformLumpSize, double profBytes) {
   if (lumpsEnd <= lumpsBegin) return;
+  ProfScope prof(st, KC_ELIM_FACTOR, 0, profBytes * batch);
   switch (uniformLumpSize) {
     case 1: launchFactorLumps<T, 1>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
     case 2: launchFactorLumps<T, 2>(st, batch, sk, data, lumpsBegin, lumpsEnd); break;
@@ -312,6 +358,14 @@ void elimFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data
 template <typename T>
 void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> data) {
   if (plan.numDst == 0) return;
+  ProfScope prof(st, KC_ELIM_GATHER, plan.gatherFlops * batch, plan.gatherBytes * sizeof(T) * batch);
+  auto fixed = [&](auto kern, int lanes) {
+    kern<<<dim3(ceilDiv(plan.numDst * lanes, 128), 1, batch), 128, 0, st>>>(plan, data);
+    B200_LAUNCH_CHECK();
+  };
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) return fixed(elim_gather_fixed_kernel<T, 6, 6, 3, 8>, 8);
+  if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3) return fixed(elim_gather_fixed_kernel<T, 3, 3, 3, 4>, 4);
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 6) return fixed(elim_gather_fixed_kernel<T, 6, 6, 6, 8>, 8);
   int E = std::min(plan.maxDstElems, 256);
   int64_t threads = plan.numDst * E;
   elim_gather_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(plan, data, E);
@@ -338,6 +392,7 @@ void assemble(cudaStream_t st, int batch, const DevSkel& sk, const int64_t* span
               int64_t numBlockRows, int64_t numBlockCols, int64_t numRows) {
   int64_t threads = numRows * srcRectWidth;
   if (threads <= 0) return;
+  ProfScope prof(st, KC_ASSEMBLE, 0, 3.0 * threads * sizeof(T) * batch);
   assemble_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(
       sk, spanToChainOffset, data, temp, rectRowBegin, dstStride, srcColDataOffset, srcRectWidth, numBlockRows,
       numBlockCols, numRows);
@@ -349,6 +404,7 @@ void elimSolveL(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan
                 int64_t ldc, int nRHS) {
   int64_t n = (plan.lumpsEnd - plan.lumpsBegin) * nRHS;
   if (n <= 0) return;
+  ProfScope prof(st, KC_SOLVE_ELIM, 0, plan.factorEntries * sizeof(T) * batch);
   elim_diag_solve_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS, plan.lumpsBegin,
                                                                              plan.lumpsEnd, false);
   B200_LAUNCH_CHECK();
@@ -366,6 +422,7 @@ void elimSolveLt(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPla
                  int64_t ldc, int nRHS) {
   int64_t n = (plan.lumpsEnd - plan.lumpsBegin) * nRHS;
   if (n <= 0) return;
+  ProfScope prof(st, KC_SOLVE_ELIM, 0, plan.factorEntries * sizeof(T) * batch);
   elim_gather_solveLt_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS,
                                                                                  plan.lumpsBegin, plan.lumpsEnd);
   B200_LAUNCH_CHECK();
@@ -395,7 +452,7 @@ void assembleVecT(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, in
 }
 
 #define B200_INSTANTIATE_SPARSE(T)                                                                                      \
-  template void elimFactorLumps<T>(cudaStream_t, int, const DevSkel&, Mats<T>, int64_t, int64_t, int);                 \
+  template void elimFactorLumps<T>(cudaStream_t, int, const DevSkel&, Mats<T>, int64_t, int64_t, int, double);                 \
   template void elimGather<T>(cudaStream_t, int, const DevElimPlan&, Mats<T>);                                          \
   template void pseudoFactorSpans<T>(cudaStream_t, int, const DevSkel&, Mats<T>, int64_t, int64_t);                    \
   template void assemble<T>(cudaStream_t, int, const DevSkel&, const int64_t*, Mats<T>, Work<T>, int64_t, int64_t,     \

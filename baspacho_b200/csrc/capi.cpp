@@ -23,6 +23,24 @@ const char* bspb200_version(void) { return "baspacho-b200 0.1 (sm_100a)"; }
 
 int64_t bspb200_launch_count(void) { return BaSpaCho::b200::launchCounter().load(); }
 
+int bspb200_profile_enable(int on) {
+  return guarded([&] { BaSpaCho::b200::profileEnable(on != 0); });
+}
+
+int64_t bspb200_profile_report(char* json_out, int64_t cap) {
+  int64_t len = -1;
+  guarded([&] {
+    std::string js = BaSpaCho::b200::profileReportJson();
+    len = (int64_t)js.size();
+    if (json_out && cap > 0) {
+      int64_t n = std::min<int64_t>(len, cap - 1);
+      std::memcpy(json_out, js.data(), n);
+      json_out[n] = 0;
+    }
+  });
+  return len;
+}
+
 int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                         const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int lower_only, void* stream) {
   return guarded([&] {

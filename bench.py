@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Solver::factor() + Solver::solve() of the supernodal sparse Cholesky.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload bal|...]
+
+One "step" = factor() + solve(nRHS=1) of ONE matrix. At N=1 the workload is BASELINE.json configs[1]: the BAL-shaped
+synthetic problem (871 cameras x 527480 points, block sizes 6/3, points eliminated by the sparse-elimination path,
+fp64). At N>1 every rank owns one such matrix (a batch of N identically structured problems sharded one per GPU,
+no data-path collective) -> weak scaling; value = algorithmic GF of all ranks / max-over-ranks device time.
+
+Timing: CUDA events on the solver's stream around factor()+solve() of every step; the in-place factor is restored
+from a pristine device copy between steps (untimed; the 0.57 GB copy also evicts L2). Inputs are larger than L2.
+`--impl reference` times the CPU restatement of the reference's BLAS backend (oracle/, kind "port": the reference
+itself cannot be compiled in this image) on the host cores, same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "factor()+solve() GF/s (algorithmic fp64 flops of the skeleton / time)"
+
+WORKLOADS = {
+    # name: (generator kind, params, (bsize_min, bsize_max), given elimination range or None, find_auto_ranges)
+    "bal": dict(kind=3, params=[527480, 871, 2, 3.28, 40, 0.1], bsize=(3, 6), n_elim=527480, auto=True,
+                desc="BAL-shaped synthetic 871 cams x 527480 points (6/3 blocks), sparse-elim {0,numPts}, fp64"),
+    "bal_small": dict(kind=3, params=[60000, 200, 2, 3.28, 40, 0.1], bsize=(3, 6), n_elim=60000, auto=True,
+                      desc="BAL-shaped synthetic 200 cams x 60000 points (6/3 blocks), sparse-elim, fp64"),
+    "grid": dict(kind=1, params=[120, 120, 1.0, 2], bsize=(6, 6), n_elim=0, auto=False,
+                 desc="GRID 120x120 block=6 conn=2 pure supernodal (no sparse elimination), fp64"),
+    "flat": dict(kind=0, params=[1000, 0.05], bsize=(3, 3), n_elim=0, auto=True,
+                 desc="FLAT size=1000 block=3 fill=0.05, fp64"),
+    "stress": dict(kind=3, params=[1000000, 200, 2, 3.0, 200, 1.0], bsize=(3, 6), n_elim=1000000, auto=True,
+                   desc="sparse-elim stress: 1M independent 3x3 points + 200 cameras, fp64"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_problem(api, wl):
+    w = WORKLOADS[wl]
+    sizes, ptrs, inds = api.gen_pattern_arrays(w["kind"], w["params"], w["bsize"][0], w["bsize"][1], 37)
+    ranges = [0, w["n_elim"]] if w["n_elim"] else []
+    return sizes, ptrs, inds, ranges, w
+
+
+def canonical_work(wl, model):
+    """algorithmic flops of the workload on the skeleton the B200 arm builds (both arms report against it)"""
+    import baspacho_b200 as bsp
+    sizes, ptrs, inds, ranges, w = gen_problem(bsp.api(), wl)
+    s = bsp.Solver.create(sizes, ptrs, inds, ranges, backend=bsp.BACKEND_SYMBOLIC_ONLY, computation_model=model,
+                          find_sparse_elim_ranges=w["auto"])
+    we = s.work_estimate()
+    return we, s
+
+
+def dist_setup(n_gpus):
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def run_reference(args):
+    """the reference's CPU path (restated BLAS backend, all host threads) on the same workload"""
+    rank, world, _ = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    from baspacho_b200 import _capi
+    from oracle import cpu as ocpu
+    api = ocpu.api()
+    cores = os.cpu_count()
+    we, _ = canonical_work(args.workload, args.model)
+    sizes, ptrs, inds, ranges, w = gen_problem(api, args.workload)
+    t0 = time.time()
+    s = ocpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=cores,
+                                 find_sparse_elim_ranges=w["auto"])
+    analysis_s = time.time() - t0
+    data0 = api.random_data_array(s.data_size, -1, 1, 37)
+    s.damp(data0, 0.0, s.order * 1.2)
+    rhs0 = api.random_data_array(s.order, -1, 1, 38).reshape(1, s.order)
+    flops = we["factor_flops"] + we["solve_flops_per_rhs"]
+    times = []
+    for it in range(args.warmup + args.steps):
+        data, x = data0.copy(), rhs0.copy()
+        t0 = time.perf_counter()
+        s.factor(data)
+        s.solve(data, x)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    value = args.steps * flops / tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "order": s.order, "analysis_s": round(analysis_s, 3)},
+        "cpu_baseline": {"value": value, "unit": "GF/s", "cores": cores, "kind": "port",
+                         "sample": "full workload (1 factor+solve per step), restated reference BackendFast: OpenBLAS "
+                                   f"{os.path.basename(ocpu.blas_path() or 'none')} + {cores} threads"},
+        "e2e": {"value": value, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_dgemm_peak(torch, dev):
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty_like(a)
+    best = 0.0
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 1:
+            best = max(best, 2 * n**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b, c
+    torch.cuda.empty_cache()
+    return best
+
+
+def run_b200(args):
+    import torch
+    import baspacho_b200 as bsp
+    rank, world, local = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    api = bsp.api()
+    sizes, ptrs, inds, ranges, w = gen_problem(api, args.workload)
+    t0 = time.time()
+    s = bsp.Solver.create(sizes, ptrs, inds, ranges, computation_model=args.model, find_sparse_elim_ranges=w["auto"])
+    analysis_s = time.time() - t0
+    stream = torch.cuda.Stream(device=dev)
+    s.set_stream(stream)
+    we = s.work_estimate()
+    flops = we["factor_flops"] + we["solve_flops_per_rhs"]
+    # every rank owns one matrix of the batch: same structure, different values
+    data_h = api.random_data_array(s.data_size, -1, 1, 37 + rank)
+    s.damp(data_h, 0.0, s.order * 1.2)
+    rhs_h = api.random_data_array(s.order, -1, 1, 38 + rank).reshape(1, s.order)
+    pin_data = torch.from_numpy(data_h).pin_memory()
+    pin_rhs = torch.from_numpy(rhs_h.copy()).pin_memory()
+    pristine = pin_data.to(dev)
+    work = torch.empty_like(pristine)
+    rhs_d = pin_rhs.to(dev)
+    x_d = torch.empty_like(rhs_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.cuda.stream(stream):
+            work.copy_(pristine, non_blocking=True)
+            x_d.copy_(rhs_d, non_blocking=True)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            s.factor(work)
+            e1.record(stream)
+            s.solve(work, x_d)
+            e2.record(stream)
+        return e0, e1, e2
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = s.launch_count()
+    t_wall = time.perf_counter()
+    evs = [step() for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = s.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    fac_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    sol_ms = [b.elapsed_time(c) for _, b, c in evs]
+    tot_s = (sum(fac_ms) + sum(sol_ms)) * 1e-3
+    t = torch.tensor([tot_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_max = float(t.item())
+
+    # residual check of the last step (result correctness inside the bench, cheap): ||A x - b|| through addMvFrom
+    y = torch.zeros_like(rhs_d)
+    with torch.cuda.stream(stream):
+        s.add_mv_from(pristine, 0, x_d, y)
+    torch.cuda.synchronize()
+    resid = float((y - rhs_d).norm() / rhs_d.norm())
+
+    # ---- e2e: the C-ABI host-buffer call (pinned host memory in, solution out), H2D + D2H inside the timed region
+    x_host = torch.empty_like(pin_rhs).pin_memory()
+    e2e_times = []
+    for it in range(2 + max(3, args.steps // 2)):
+        x_host.copy_(pin_rhs)
+        barrier()
+        t0 = time.perf_counter()
+        s.factor_solve_host(pin_data, x_host, None)
+        dt = time.perf_counter() - t0
+        if it >= 2:
+            e2e_times.append(dt)
+    te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel-class profile of one more step (events around every launch of our kernels)
+    api.profile(True)
+    step()
+    torch.cuda.synchronize()
+    prof = api.profile_json()
+    api.profile(False)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    dgemm_peak = measure_dgemm_peak(torch, dev)
+    g = prof["gemm"]
+    gemm_tf = g["flops"] / max(g["ms"], 1e-9) / 1e9
+    roofline = {"kernel": "gemm_nt_f64_kernel (DMMA m8n8k4 SYRK/GEMM tiles of the blocked supernode Cholesky)",
+                "bound": "tensor", "achieved": gemm_tf, "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": gemm_tf / dgemm_peak if dgemm_peak else None, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json holds no fp64 figure; "
+                               "tcgen05 has no f64 kind, DMMA is the fp64 tensor path)",
+                "launches_per_step": g["launches"], "share_of_step_ms": g["ms"]}
+    eg, ef = prof["elim_gather"], prof["elim_factor"]
+    roofline_hbm = None
+    if ef["launches"]:
+        roofline_hbm = {"kernels": "elim_factor_lumps + elim_gather (sparse elimination)", "bound": "hbm",
+                        "achieved": (ef["bytes"] + eg["bytes"]) / max(ef["ms"] + eg["ms"], 1e-9) / 1e6,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (ef["bytes"] + eg["bytes"]) / max(ef["ms"] + eg["ms"], 1e-9) / 1e6 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
+                        "ms": ef["ms"] + eg["ms"]}
+
+    # ---- CPU baseline (oracle port of the reference's BLAS backend) on a bounded sample: the full workload once
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        try:
+            from baspacho_b200 import _capi
+            from oracle import cpu as ocpu
+            cores = os.cpu_count()
+            o = ocpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=cores,
+                                         find_sparse_elim_ranges=w["auto"])
+            d = ocpu.api().random_data_array(o.data_size, -1, 1, 37)
+            o.damp(d, 0.0, o.order * 1.2)
+            xr = rhs_h.copy()
+            t0 = time.perf_counter()
+            o.factor(d)
+            o.solve(d, xr)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": flops / dt / 1e9, "unit": "GF/s", "cores": cores, "kind": "port",
+                            "sample": f"full workload, 1 factor+solve ({dt:.2f} s), restated reference BackendFast (OpenBLAS + threads)",
+                            "solution_max_abs_diff_vs_gpu": float(np.abs(xr - x_d.cpu().numpy()).max())}
+        except Exception as e:  # the baseline must never take the GPU number down
+            cpu_baseline = {"value": None, "unit": "GF/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    value = world * args.steps * flops / tot_max / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"] + (f"; batch of {world} such matrices sharded 1 per GPU" if world > 1 else ""),
+                   "order": s.order, "data_size": s.data_size, "nnz_l": we["nnz_l"], "factor_gflop": we["factor_flops"] / 1e9,
+                   "solve_gflop": we["solve_flops_per_rhs"] / 1e9, "n_rhs": 1, "lumps": s.num_lumps,
+                   "dense_lump_sizes": np.diff(s.lumpStart[w["n_elim"]:]).tolist()[-8:] if w["n_elim"] else None,
+                   "l2_policy": "inputs (0.57 GB factor) larger than L2; factor restored from a pristine copy between steps",
+                   "timing": "cuda events per step on the solver stream; sum over steps; max over ranks",
+                   "analysis_s": round(analysis_s, 3)},
+        "factor_ms": float(np.mean(fac_ms)), "solve_ms": float(np.mean(sol_ms)),
+        "factor_gfs": we["factor_flops"] / (np.mean(fac_ms) * 1e-3) / 1e9,
+        "residual": resid, "wall_s_timed_region": t_wall,
+        "gpu_launches": launches,
+        "e2e": {"value": world * flops / e2e_s / 1e9, "unit": "GF/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(pin_data.numel() * 8 + pin_rhs.numel() * 8),
+                "d2h_bytes_per_step": int(pin_rhs.numel() * 8),
+                "api": "bspb200_factor_solve_host (C ABI, pinned host buffers)"},
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "kernel_classes": prof,
+        "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bal", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", type=int, default=2, help="supernode-merge cost model preset (2 = B200)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

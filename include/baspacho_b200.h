@@ -120,6 +120,11 @@ int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha
 /* in-place Cholesky of the (n + rows_below) x n trapezoid (top n x n = diagonal block, lower triangle), ld >= n */
 int bspb200_dev_potrf(int dtype, int64_t n, int64_t rows_below, void* A, int64_t ld, void* stream);
 
+/* per-kernel-class profiling (CUDA events around every launch, algorithmic flops/bytes beside the time); the
+ * report is a JSON object {class: {launches, ms, flops, bytes}}; returns its length (copied up to cap-1 + NUL) */
+int bspb200_profile_enable(int on);
+int64_t bspb200_profile_report(char* json_out, int64_t cap);
+
 /* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
 int64_t bspb200_launch_count(void);
 

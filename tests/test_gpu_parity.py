@@ -20,6 +20,9 @@ def torch_of(a):
 
 
 def make_pair(sizes, ptrs, inds, ranges=(), **kw):
+    # createSolver picks the supernode-merge cost model from the backend (reference Solver.cpp:679-683): pin one model
+    # so that the device solver and the CPU checker build the same skeleton
+    kw.setdefault("computation_model", _capi.MODEL_CUDA_2080TI)
     g = bsp.Solver.create(sizes, ptrs, inds, ranges, **kw)
     o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_REF, **kw)
     for name in _capi.ARRAY_IDS:  # the index structure both sides work on is identical, bit for bit
