@@ -81,6 +81,15 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 
   const int KT = (int)((s.k + BK - 1) / BK);
 
+  if (beta != 0.0) {  // pull the C tile towards L2 while the main loop runs (one 128-byte line per request)
+    constexpr int LPR = BN * 8 / 128;  // lines per tile row
+    for (int i = tid; i < BM * LPR; i += NT) {
+      const int64_t row = m0 + i / LPR, col = n0 + (i % LPR) * 16;
+      if (row < s.m && col < s.n && !(s.lowerOnly && col > row))
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(C + row * s.ldc + col));
+    }
+  }
+
   auto loadTile = [&](int stage, int kt) {
     const int64_t k0 = (int64_t)kt * BK;
     constexpr int CPR = BK / VEC;  // chunks per row
@@ -136,24 +145,38 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   }
   cpAsyncWait<0>();
 
-  // epilogue: each thread owns 2 consecutive columns of every 8x8 tile
+  // epilogue: each thread owns 2 consecutive columns of every 8x8 tile. With beta != 0 the old C values of tile row
+  // i + 1 are loaded before tile row i is stored (software pipelined: the read-modify-write never waits on a
+  // load it has just issued); the C tile was prefetched into L2 at kernel start.
+  auto valid = [&](int i, int j, int e, int64_t& off) {
+    const int64_t row = m0 + wm + i * 8 + g, c = n0 + wn + j * 8 + 2 * t + e;
+    off = row * s.ldc + c;
+    return row < s.m && c < s.n && !(s.lowerOnly && c > row);
+  };
+  double cold[2][TN][2];
+  auto loadRow = [&](int i, double (*dst)[2]) {
 #pragma unroll
-  for (int i = 0; i < TM; i++) {
-    int64_t row = m0 + wm + i * 8 + g;
-    if (row >= s.m) continue;
-#pragma unroll
-    for (int j = 0; j < TN; j++) {
-      int64_t col = n0 + wn + j * 8 + 2 * t;
+    for (int j = 0; j < TN; j++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        int64_t c = col + e;
-        if (c >= s.n || (s.lowerOnly && c > row)) continue;
-        double* dst = C + row * s.ldc + c;
-        double v = alpha * acc[i][j][e];
-        if (beta != 0.0) v += beta * *dst;
-        *dst = v;
+        int64_t off;
+        dst[j][e] = valid(i, j, e, off) ? C[off] : 0.0;
       }
-    }
+  };
+  if (beta != 0.0) loadRow(0, cold[0]);
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    if (beta != 0.0 && i + 1 < TM) loadRow(i + 1, cold[(i + 1) & 1]);
+#pragma unroll
+    for (int j = 0; j < TN; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int64_t off;
+        if (!valid(i, j, e, off)) continue;
+        double v = alpha * acc[i][j][e];
+        if (beta != 0.0) v += beta * cold[i & 1][j][e];
+        C[off] = v;
+      }
   }
 }
 
@@ -223,66 +246,73 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(GemmShape s, T alpha,
 // Diagonal block (n <= kNB) + the rows below it, in ONE launch:
 //   DO_POTRF: every CTA loads the n x n diagonal block and factors it (redundantly: the other SMs would idle anyway,
 //   and it removes a dependent launch + a reload of L); CTA 0 writes the factor back.
-//   Then CTA b solves X L^T = B for rows [R b, R b + R), R = 128 / G: G adjacent lanes share one row, each owns
-//   32/G columns of the current 32-column chunk in registers; L is read from shared memory as broadcast vector loads.
+//   Then CTA b solves X L^T = B for rows [64 b, 64 b + 64): 4 adjacent lanes share one row, each owns 8 columns of
+//   the current 32-column chunk in registers.
 // Cholesky phase: register resident, right looking. Thread (warp w, lane l) owns the entries (i, c) with
-//   i = l + 32 a (a < 3), c = w + 4 u (u < 24). Per column its owner warp publishes it (unscaled) to a double-buffered
+//   i = l + 32 a (a < 3), c = w + 8 u (u < 12). Per column its owner warp publishes it (unscaled) to a double-buffered
 //   shared column, ONE barrier, then every thread updates its own registers with 1/pivot folded into the row operand.
 //   The column loop is unrolled over u so that every register index is static.
-constexpr int kNB = 96;          // max diagonal block
-constexpr int kLDS = 100;        // smem row stride of the block: rows 16-byte aligned for the vector loads (fp32 and fp64)
-constexpr int kPanelThreads = 128;
-constexpr int kLDX = 97;         // smem row stride of the row slab: odd (per-row walks are conflict free)
+// Solve phase: L is kept TRANSPOSED in shared memory, Lt[q][c] = L[c][q], each 8-column piece padded to 10 entries:
+//   the 4 lanes of a row read 4 x 64 contiguous-ish bytes per q with 16-byte loads and no bank conflict.
+constexpr int kNB = 96;            // max diagonal block
+constexpr int kLDS = 100;          // row stride of the row-major staging of the diagonal block
+constexpr int kLDT = 120;          // row stride of Lt: 12 pieces x (8 + 2 pad)
+constexpr int kLDX = 98;           // row stride of the row slab (even: 16-byte aligned rows, conflict-free 8-row walks)
+constexpr int kPanelThreads = 256;
+constexpr int kPanelG = 4;         // lanes per row in the solve phase
+constexpr int kPanelRows = kPanelThreads / kPanelG;
+
+__device__ __forceinline__ int ltPos(int c) { return (c >> 3) * 10 + (c & 7); }  // column -> padded position in an Lt row
 
 template <typename T>
-struct Vec4 {
-  T v[4];
+struct Vec2 {
+  T v[2];
 };
-__device__ __forceinline__ Vec4<double> load4(const double* p) {
-  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
-  return {{a.x, a.y, b.x, b.y}};
+__device__ __forceinline__ Vec2<double> load2(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  return {{a.x, a.y}};
 }
-__device__ __forceinline__ Vec4<float> load4(const float* p) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  return {{a.x, a.y, a.z, a.w}};
+__device__ __forceinline__ Vec2<float> load2(const float* p) {
+  const float2 a = *reinterpret_cast<const float2*>(p);
+  return {{a.x, a.y}};
 }
 
-template <typename T, bool DO_POTRF, int G>
+template <typename T, bool DO_POTRF>
 __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
                                                              Operand<T> Bop, int64_t ldb) {
-  constexpr int NW = kPanelThreads / 32;  // 4 warps
-  constexpr int R = kPanelThreads / G;    // rows per CTA
-  constexpr int W = 32 / G;               // columns of a chunk per thread
+  constexpr int NW = kPanelThreads / 32;  // 8 warps
+  constexpr int G = kPanelG, R = kPanelRows, W = 32 / G;
+  constexpr int LA = kNB / NW, LU = kNB / 32;
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  T* S = reinterpret_cast<T*>(smemRaw);  // [kNB][kLDS], zero padded
-  T* invd = S + kNB * kLDS;              // [kNB]
-  T* Xs = invd + kNB;                    // [R][kLDX]  (also the 2 x kNB column buffer of the Cholesky phase)
+  T* Lt = reinterpret_cast<T*>(smemRaw);  // [kNB][kLDT] transposed factor (first used as row-major staging [kNB][kLDS])
+  T* invd = Lt + kNB * kLDT;              // [kNB]
+  T* Xs = invd + kNB;                     // [R][kLDX]  (also the 2 x kNB column buffer of the Cholesky phase)
   T* __restrict__ L = Lop.at(blockIdx.z);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < kNB * kLDS + kNB; i += kPanelThreads) S[i] = T(0);
-  __syncthreads();
-  {  // lower triangle -> smem, all loads in flight at once
-    T tmp[(kNB / NW) * (kNB / 32)];
-#pragma unroll
-    for (int a = 0; a < kNB / NW; a++)
-#pragma unroll
-      for (int u = 0; u < kNB / 32; u++) {
-        const int r = warp + NW * a, c = lane + 32 * u;
-        tmp[a * (kNB / 32) + u] = (c <= r && r < n) ? L[(int64_t)r * ldl + c] : T(0);
-      }
-#pragma unroll
-    for (int a = 0; a < kNB / NW; a++)
-#pragma unroll
-      for (int u = 0; u < kNB / 32; u++) {
-        const int r = warp + NW * a, c = lane + 32 * u;
-        if (c <= r && r < n) S[r * kLDS + c] = tmp[a * (kNB / 32) + u];
-      }
-  }
-  __syncthreads();
-
   if (DO_POTRF) {
-    constexpr int RA = kNB / 32, CU = kNB / NW;  // 3 row slots, 24 column slots
+    constexpr int RA = kNB / 32, CU = kNB / NW;  // 3 row slots, 12 column slots per thread
+    T* S = Lt;
+    for (int i = tid; i < kNB * kLDS; i += kPanelThreads) S[i] = T(0);
+    __syncthreads();
+    {  // lower triangle -> smem (coalesced), all loads in flight at once
+      T tmp[LA * LU];
+#pragma unroll
+      for (int a = 0; a < LA; a++)
+#pragma unroll
+        for (int u = 0; u < LU; u++) {
+          const int r = warp + NW * a, c = lane + 32 * u;
+          tmp[a * LU + u] = (c <= r && r < n) ? L[(int64_t)r * ldl + c] : T(0);
+        }
+#pragma unroll
+      for (int a = 0; a < LA; a++)
+#pragma unroll
+        for (int u = 0; u < LU; u++) {
+          const int r = warp + NW * a, c = lane + 32 * u;
+          if (c <= r && r < n) S[r * kLDS + c] = tmp[a * LU + u];
+        }
+    }
+    __syncthreads();
     T* colbuf = Xs;
     T reg[RA][CU];
 #pragma unroll
@@ -301,20 +331,25 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t row
             if (lane + 32 * a >= j) cb[lane + 32 * a] = reg[a][u];
         }
         __syncthreads();
+        // operands of the rank-1 update: all shared loads issued before any use. Entries above the diagonal of the
+        // register tile are never read, so the update needs no (row >= column) predicate; finished rows get li = 0.
+        T scv[CU], li[RA];
+#pragma unroll
+        for (int u2 = u; u2 < CU; u2++) scv[u2] = cb[warp + NW * u2];
+#pragma unroll
+        for (int a = 0; a < RA; a++) li[a] = cb[lane + 32 * a];
         const T piv = cb[j];
         const T rs = rsqrt(piv);
         const T invp = rs * rs;
-        T li[RA];
 #pragma unroll
-        for (int a = 0; a < RA; a++) li[a] = (lane + 32 * a > j) ? cb[lane + 32 * a] * invp : T(0);
+        for (int a = 0; a < RA; a++) li[a] = (lane + 32 * a > j) ? li[a] * invp : T(0);
+        if (warp <= w) scv[u] = T(0);  // columns <= j of this slot are finished (or the pivot column itself)
 #pragma unroll
-        for (int u2 = u; u2 < CU; u2++) {
-          const int c = warp + NW * u2;
-          if (c > j) {  // warp uniform
-            const T sc = cb[c];
+        for (int a = 0; a < RA; a++) {
+          if (j < 32 * a + 31) {  // some row of the slot is still active (warp uniform)
 #pragma unroll
-            for (int a = 0; a < RA; a++)
-              if (c <= lane + 32 * a) reg[a][u2] -= li[a] * sc;
+            for (int u2 = u; u2 < CU; u2++)
+              if (NW * u2 <= 32 * a + 31) reg[a][u2] -= li[a] * scv[u2];  // static: the tile touches the lower triangle
           }
         }
         if (warp == w) {
@@ -327,56 +362,80 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t row
         }
       }
     }
-    __syncthreads();  // the column buffers are no longer read
+    __syncthreads();  // column buffers and the row-major staging are dead
+    for (int i = tid; i < kNB * kLDT + kNB; i += kPanelThreads) Lt[i] = T(0);
+    __syncthreads();
 #pragma unroll
     for (int a = 0; a < RA; a++)
 #pragma unroll
       for (int u = 0; u < CU; u++) {
         const int i = lane + 32 * a, c = warp + NW * u;
-        if (c <= i && i < n) S[i * kLDS + c] = reg[a][u];
-      }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-#pragma unroll
-      for (int a = 0; a < kNB / NW; a++)
-#pragma unroll
-        for (int u = 0; u < kNB / 32; u++) {
-          const int r = warp + NW * a, c = lane + 32 * u;
-          if (c <= r && r < n) L[(int64_t)r * ldl + c] = S[r * kLDS + c];
+        if (c <= i && i < n) {
+          Lt[c * kLDT + ltPos(i)] = reg[a][u];
+          if (blockIdx.x == 0) L[(int64_t)i * ldl + c] = reg[a][u];
         }
-    }
+      }
+  } else {
+    for (int i = tid; i < kNB * kLDT + kNB; i += kPanelThreads) Lt[i] = T(0);
+    __syncthreads();
+    // Lt[c][r] = L[r][c]: lanes walk down a column (strided global reads, L2 resident; conflict-free smem writes)
+#pragma unroll 4
+    for (int c = warp; c < n; c += NW)
+#pragma unroll
+      for (int u = 0; u < LU; u++) {
+        const int r = lane + 32 * u;
+        if (r >= c && r < n) Lt[c * kLDT + ltPos(r)] = L[(int64_t)r * ldl + c];
+      }
   }
   if (rows <= 0) return;
-  if (tid < n) invd[tid] = T(1) / S[tid * kLDS + tid];
+  __syncthreads();
+  if (tid < n) invd[tid] = T(1) / Lt[tid * kLDT + ltPos(tid)];
 
   T* __restrict__ B = Bop.at(blockIdx.z);
   const int64_t r0 = (int64_t)blockIdx.x * R;
   const int nr = (int)min((int64_t)R, rows - r0);
-  for (int r = warp; r < nr; r += NW)
+  {  // row slab -> smem, all loads in flight at once
+    constexpr int RW = R / NW;
+    T tmp[RW * LU];
 #pragma unroll
-    for (int u = 0; u < kNB / 32; u++) {
-      const int c = lane + 32 * u;
-      if (c < n) Xs[r * kLDX + c] = B[(r0 + r) * ldb + c];
-    }
+    for (int a = 0; a < RW; a++)
+#pragma unroll
+      for (int u = 0; u < LU; u++) {
+        const int r = warp + NW * a, c = lane + 32 * u;
+        tmp[a * LU + u] = (r < nr && c < n) ? B[(r0 + r) * ldb + c] : T(0);
+      }
+#pragma unroll
+    for (int a = 0; a < RW; a++)
+#pragma unroll
+      for (int u = 0; u < LU; u++) Xs[(warp + NW * a) * kLDX + lane + 32 * u] = tmp[a * LU + u];
+  }
   __syncthreads();
   {
     const int row = tid / G, g = tid % G;  // G adjacent lanes share a row
-    const bool live = row < nr;
-    T* x = Xs + (live ? row : 0) * kLDX;
+    T* x = Xs + row * kLDX;
     for (int c0 = 0; c0 < n; c0 += 32) {
-      const int cg = c0 + g * W;  // first column of this thread's piece
+      const int cg = c0 + g * W;           // first column of this thread's piece
+      const int pg = ltPos(cg);            // its padded position in an Lt row
       T acc[W];
 #pragma unroll
-      for (int k = 0; k < W; k++) acc[k] = (cg + k < n) ? x[cg + k] : T(0);
-      for (int q0 = 0; q0 < c0; q0 += 4) {
-        const T x0 = x[q0], x1 = x[q0 + 1], x2 = x[q0 + 2], x3 = x[q0 + 3];
+      for (int k = 0; k < W; k++) acc[k] = x[cg + k];
+#pragma unroll 2
+      for (int q0 = 0; q0 < c0; q0 += 2) {
+        const Vec2<T> xq = load2(x + q0);
+        Vec2<T> l0[W / 2], l1[W / 2];
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-          const Vec4<T> l = load4(S + (cg + k) * kLDS + q0);
-          acc[k] -= x0 * l.v[0];
-          acc[k] -= x1 * l.v[1];
-          acc[k] -= x2 * l.v[2];
-          acc[k] -= x3 * l.v[3];
+        for (int k = 0; k < W / 2; k++) l0[k] = load2(Lt + q0 * kLDT + pg + 2 * k);
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) l1[k] = load2(Lt + (q0 + 1) * kLDT + pg + 2 * k);
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+          acc[2 * k] -= xq.v[0] * l0[k].v[0];
+          acc[2 * k + 1] -= xq.v[0] * l0[k].v[1];
+        }
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+          acc[2 * k] -= xq.v[1] * l1[k].v[0];
+          acc[2 * k + 1] -= xq.v[1] * l1[k].v[1];
         }
       }
       // triangular part of the chunk, piece by piece: piece p is finished by its owner lane, broadcast with shuffles
@@ -388,7 +447,7 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t row
           for (int k = 0; k < W; k++) {
             acc[k] *= invd[cg + k];
 #pragma unroll
-            for (int k2 = k + 1; k2 < W; k2++) acc[k2] -= acc[k] * S[(cg + k2) * kLDS + cg + k];
+            for (int k2 = k + 1; k2 < W; k2++) acc[k2] -= acc[k] * Lt[(cg + k) * kLDT + pg + k2];
           }
         }
         if (p + 1 < G) {
@@ -396,25 +455,23 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t row
           for (int m = 0; m < W; m++) {
             const T xp = __shfl_sync(0xffffffffu, acc[m], (lane / G) * G + p);
             if (g > p) {
+              const T* lrow = Lt + (c0 + p * W + m) * kLDT + pg;
 #pragma unroll
-              for (int k = 0; k < W; k++) acc[k] -= xp * S[(cg + k) * kLDS + c0 + p * W + m];
+              for (int k = 0; k < W; k++) acc[k] -= xp * lrow[k];
             }
           }
         }
       }
       __syncwarp();
-      if (live) {
 #pragma unroll
-        for (int k = 0; k < W; k++)
-          if (cg + k < n) x[cg + k] = acc[k];
-      }
+      for (int k = 0; k < W; k++) x[cg + k] = acc[k];
       __syncwarp();
     }
   }
   __syncthreads();
   for (int r = warp; r < nr; r += NW)
 #pragma unroll
-    for (int u = 0; u < kNB / 32; u++) {
+    for (int u = 0; u < LU; u++) {
       const int c = lane + 32 * u;
       if (c < n) B[(r0 + r) * ldb + c] = Xs[r * kLDX + c];
     }
@@ -498,27 +555,16 @@ int maxBlockDim<float>() {
   return kNB;
 }
 
-template <typename T, bool DO_POTRF, int G>
-static void launchPanelG(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
-                         int64_t ldb) {
-  constexpr int R = kPanelThreads / G;
-  size_t smem = ((size_t)kNB * kLDS + kNB + std::max<size_t>((size_t)R * kLDX, 2 * kNB)) * sizeof(T);
-  static bool once = (setSmem(panel_kernel<T, DO_POTRF, G>, smem), true);
-  (void)once;
-  int ctas = std::max(1, ceilDiv(rows, R));
-  panel_kernel<T, DO_POTRF, G><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb);
-  B200_LAUNCH_CHECK();
-}
-
 template <typename T, bool DO_POTRF>
 static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                         int64_t ldb) {
   if (n > kNB) throw std::runtime_error("panel kernel: block too large");
-  // rows per CTA: 32 (4 lanes per row) unless there are so many rows that 64 per CTA still fills the machine
-  if (rows * batch > 64 * 296)
-    launchPanelG<T, DO_POTRF, 2>(st, batch, n, rows, L, ldl, B, ldb);
-  else
-    launchPanelG<T, DO_POTRF, 4>(st, batch, n, rows, L, ldl, B, ldb);
+  size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
+  static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
+  (void)once;
+  int ctas = std::max(1, ceilDiv(rows, kPanelRows));
+  panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb);
+  B200_LAUNCH_CHECK();
 }
 
 template <typename T>

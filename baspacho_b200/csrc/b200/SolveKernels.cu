@@ -312,18 +312,28 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
     if (!TR) {
       const int64_t rbeg = j0 + jb + (int64_t)blockIdx.x * kStepRows;
       constexpr int RPW = kStepRows / kTrsvWarps;  // rows per warp
-#pragma unroll 4
-      for (int rr = 0; rr < RPW; rr++) {
-        const int64_t row = rbeg + warp * RPW + rr;
-        if (row >= n) break;
-        const T* m = L + row * ldl + j0;
-        T mv[3];
+      constexpr int RB = 8;                        // rows in flight per warp
+      for (int rr0 = 0; rr0 < RPW; rr0 += RB) {
+        const int64_t rowBase = rbeg + warp * RPW + rr0;
+        if (rowBase >= n) break;
+        T mv[RB][3];
 #pragma unroll
-        for (int u = 0; u < 3; u++) mv[u] = (lane + 32 * u < jb) ? m[lane + 32 * u] : T(0);
+        for (int rr = 0; rr < RB; rr++)
+#pragma unroll
+          for (int u = 0; u < 3; u++)
+            mv[rr][u] = (rowBase + rr < n && lane + 32 * u < jb) ? L[(rowBase + rr) * ldl + j0 + lane + 32 * u] : T(0);
         for (int q = 0; q < ng; q++) {
-          T v = mv[0] * xs[q * kTB + lane] + mv[1] * xs[q * kTB + lane + 32] + mv[2] * xs[q * kTB + lane + 64];
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) C[(int64_t)(g0 + q) * ldc + row] -= v;
+          const T x0 = xs[q * kTB + lane], x1 = xs[q * kTB + lane + 32], x2 = xs[q * kTB + lane + 64];
+          T v[RB];
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++) v[rr] = mv[rr][0] * x0 + mv[rr][1] * x1 + mv[rr][2] * x2;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) v[rr] += __shfl_xor_sync(0xffffffffu, v[rr], o);
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++)
+            if (lane == rr && rowBase + rr < n) C[(int64_t)(g0 + q) * ldc + rowBase + rr] -= v[rr];
         }
       }
     } else {
