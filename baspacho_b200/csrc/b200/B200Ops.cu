@@ -30,7 +30,7 @@ struct B200SyncOps {
 struct B200SymElimCtx : SymElimCtx {
   ElimPlan host;  // index vectors are released after upload; scalars stay
   DevBuf<int64_t> dstOff, rowChainOff;
-  DevBuf<int32_t> dstStride, dstTaskPtr, rowPtr, rowChainCol;
+  DevBuf<int32_t> dstStride, dstTaskPtr, rowPtr, rowChainCol, lightList, heavyList;
   DevBuf<int16_t> dstRows, dstCols, rowChainK;
   DevBuf<uint32_t> taskA, taskB;
   DevBuf<uint16_t> taskK;
@@ -99,6 +99,9 @@ struct B200SymbolicCtx : SymbolicCtx {
     d.factorEntries = p.factorEntries, d.gatherFlops = p.gatherFlops, d.gatherBytes = p.gatherEntries;
     d.numDst = p.numDst(), d.maxDstElems = p.maxDstElems;
     d.uniRows = p.uniRows, d.uniCols = p.uniCols, d.uniK = p.uniK;
+    e->lightList.upload(p.lightList), e->heavyList.upload(p.heavyList);
+    d.lightList = e->lightList.ptr(), d.heavyList = e->heavyList.ptr();
+    d.numLight = (int64_t)p.lightList.size(), d.numHeavy = (int64_t)p.heavyList.size();
     d.dstOff = e->dstOff.ptr(), d.dstStride = e->dstStride.ptr(), d.dstRows = e->dstRows.ptr();
     d.dstCols = e->dstCols.ptr(), d.dstTaskPtr = e->dstTaskPtr.ptr(), d.taskA = e->taskA.ptr();
     d.taskB = e->taskB.ptr(), d.taskK = e->taskK.ptr();
@@ -107,7 +110,8 @@ struct B200SymbolicCtx : SymbolicCtx {
     d.rowChainK = e->rowChainK.ptr();
     // keep only the scalars on the host
     for (auto* v : {&p.dstOff, &p.rowChainOff}) vector<int64_t>().swap(*v);
-    for (auto* v : {&p.dstStride, &p.dstTaskPtr, &p.rowPtr, &p.rowChainCol}) vector<int32_t>().swap(*v);
+    for (auto* v : {&p.dstStride, &p.dstTaskPtr, &p.rowPtr, &p.rowChainCol, &p.lightList, &p.heavyList})
+      vector<int32_t>().swap(*v);
     for (auto* v : {&p.dstRows, &p.dstCols, &p.rowChainK}) vector<int16_t>().swap(*v);
     for (auto* v : {&p.taskA, &p.taskB}) vector<uint32_t>().swap(*v);
     vector<uint16_t>().swap(p.taskK);

@@ -31,6 +31,9 @@ struct ElimPlan {
   std::vector<uint16_t> taskK;      // width of the source lump
   int maxDstElems = 0;
   int uniRows = 0, uniCols = 0, uniK = 0;  // > 0 when every destination / task has these dimensions
+  // destinations split by task count: light ones are summed by a few lanes, heavy ones by a whole CTA
+  static constexpr int kHeavyTasks = 512;
+  std::vector<int32_t> lightList, heavyList;
 
   // row view for the triangular solves: per row span >= spanRowBegin, the chains found in that row
   std::vector<int32_t> rowPtr;        // per row span - spanRowBegin (+1)

@@ -34,6 +34,9 @@ struct DevElimPlan {
   int64_t numDst;
   int maxDstElems;
   int uniRows, uniCols, uniK;
+  const int32_t* lightList;
+  const int32_t* heavyList;
+  int64_t numLight, numHeavy;
   const int64_t* dstOff;
   const int32_t* dstStride;
   const int16_t* dstRows;

@@ -602,6 +602,23 @@ static void potrfRec(cudaStream_t st, int batch, int64_t totalRows, int64_t c0, 
   }
   int64_t blocks = (w + nb - 1) / nb;  // >= 2
   int64_t w1 = (blocks / 2) * nb;      // left width: a multiple of the block size, < w
+  {
+    // wave-aware split: the trailing update runs one 128x128 tile per CTA, one CTA per SM; among the splits near
+    // the middle pick the one whose tile count fills whole waves of the 148 SMs best
+    auto tiles = [&](int64_t left) {
+      int64_t m = totalRows - (c0 + left), n2 = w - left;
+      int64_t tn = (n2 + 127) / 128, tm = (m + 127) / 128;
+      return tn * (tn + 1) / 2 + (tm - tn) * tn;
+    };
+    double best = -1;
+    for (int64_t b = std::max<int64_t>(1, blocks * 3 / 10); b <= std::min(blocks - 1, blocks * 7 / 10); b++) {
+      int64_t t = tiles(b * nb) * batch;
+      if (t < 148) continue;
+      double eff = (double)t / (148.0 * ((t + 147) / 148));
+      eff -= 0.002 * std::abs((double)(2 * b - blocks));  // mild preference for balanced halves
+      if (eff > best) best = eff, w1 = b * nb;
+    }
+  }
   potrfRec<T>(st, batch, totalRows, c0, w1, A, ld);
   // rows below the left diagonal block: panel P = A[c0+w1 .., c0 .. c0+w1); update A[c0+w1.., c0+w1 .. c0+w) -= P P1^T
   int64_t r0 = c0 + w1, m = totalRows - r0, n = w - w1;

@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
   T* C = Cop.at(blockIdx.z);
   T* X = Xop.at(blockIdx.z);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kTB * kTLD + kTB; i += kTrsvWarps * 32) Ls[i] = T(0);  // zero padding (block < 96, invd)
+  __syncthreads();
   {
     const T* D = L + j0 * ldl + j0;
     T tmp[(kTB / kTrsvWarps) * 3];
@@ -272,26 +274,34 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
       T x[3];
 #pragma unroll
       for (int u = 0; u < 3; u++) x[u] = (lane + 32 * u < jb) ? c[lane + 32 * u] : T(0);
+      T dinv[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++) dinv[u] = invd[lane + 32 * u];  // zero beyond jb
       if (!TR) {
 #pragma unroll
-        for (int uj = 0; uj < 3; uj++)
-          for (int jj = 0; jj < 32 && 32 * uj + jj < jb; jj++) {
+        for (int uj = 0; uj < 3; uj++) {
+          if (32 * uj >= jb) break;
+#pragma unroll 8
+          for (int jj = 0; jj < 32; jj++) {
             const int j = 32 * uj + jj;
-            const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+            // the pivot entry is scaled by its own lane before the broadcast (one shuffle on the critical path)
+            const T xj = __shfl_sync(0xffffffffu, x[uj] * dinv[uj], jj);
             if (lane == jj) x[uj] = xj;
 #pragma unroll
             for (int u = uj; u < 3; u++) {
               const int i = lane + 32 * u;
-              if (i > j && i < jb) x[u] -= Ls[i * kTLD + j] * xj;
+              if (i > j) x[u] -= Ls[i * kTLD + j] * xj;
             }
           }
+        }
       } else {
 #pragma unroll
-        for (int uj = 2; uj >= 0; uj--)
+        for (int uj = 2; uj >= 0; uj--) {
+          if (32 * uj >= jb) continue;
+#pragma unroll 8
           for (int jj = 31; jj >= 0; jj--) {
             const int j = 32 * uj + jj;
-            if (j >= jb) continue;
-            const T xj = __shfl_sync(0xffffffffu, x[uj], jj) * invd[j];
+            const T xj = __shfl_sync(0xffffffffu, x[uj] * dinv[uj], jj);
             if (lane == jj) x[uj] = xj;
 #pragma unroll
             for (int u = 0; u <= uj; u++) {
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
               if (i < j) x[u] -= Ls[j * kTLD + i] * xj;
             }
           }
+        }
       }
 #pragma unroll
       for (int u = 0; u < 3; u++) {

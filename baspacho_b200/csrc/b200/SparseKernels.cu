@@ -112,20 +112,28 @@ __global__ void __launch_bounds__(256) elim_gather_kernel(DevElimPlan p, Mats<T>
 // partial product in registers (each block is read once, 8-byte loads of consecutive addresses per lane), then a
 // fixed-order butterfly over the LANES lanes and one read-modify-write of the target per entry.
 template <typename T, int NR, int NC, int K, int LANES>
-__global__ void __launch_bounds__(128) elim_gather_fixed_kernel(DevElimPlan p, Mats<T> mats) {
+__global__ void __launch_bounds__(LANES > 32 ? LANES : 128)
+    elim_gather_fixed_kernel(DevElimPlan p, Mats<T> mats, const int32_t* __restrict__ list, int64_t count) {
+  // LANES <= 32: LANES adjacent lanes per destination; LANES > 32: the whole CTA (LANES threads) on one destination
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t d = gid / LANES;
+  const int64_t slot = gid / LANES;
   const int sub = (int)(gid % LANES);
-  const bool live = d < p.numDst;
+  const bool live = slot < count;
+  const int64_t d = live ? list[slot] : 0;
   T* data = mats.at(blockIdx.z);
   T acc[NR * NC];
 #pragma unroll
   for (int e = 0; e < NR * NC; e++) acc[e] = T(0);
   if (live) {
     const int tEnd = p.dstTaskPtr[d + 1];
-    for (int t = p.dstTaskPtr[d] + sub; t < tEnd; t += LANES) {
-      const T* __restrict__ a = data + p.taskA[t];
-      const T* __restrict__ b = data + p.taskB[t];
+    int t = p.dstTaskPtr[d] + sub;
+    uint32_t oa = 0, ob = 0;
+    if (t < tEnd) oa = p.taskA[t], ob = p.taskB[t];
+    while (t < tEnd) {
+      const T* __restrict__ a = data + oa;
+      const T* __restrict__ b = data + ob;
+      const int tn = t + LANES;
+      if (tn < tEnd) oa = p.taskA[tn], ob = p.taskB[tn];  // next task's offsets in flight with this task's blocks
       T av[NC * K], bv[NR * K];
 #pragma unroll
       for (int i = 0; i < NC * K; i++) av[i] = a[i];
@@ -137,13 +145,29 @@ __global__ void __launch_bounds__(128) elim_gather_fixed_kernel(DevElimPlan p, M
         for (int c = 0; c < NC; c++)
 #pragma unroll
           for (int q = 0; q < K; q++) acc[r * NC + c] += bv[r * K + q] * av[c * K + q];
+      t = tn;
     }
   }
+  constexpr int WL = LANES > 32 ? 32 : LANES;
 #pragma unroll
-  for (int o = 1; o < LANES; o <<= 1)
+  for (int o = 1; o < WL; o <<= 1)
 #pragma unroll
     for (int e = 0; e < NR * NC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-  if (live) {
+  if constexpr (LANES > 32) {
+    __shared__ T red[LANES / 32][NR * NC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++)
+      if (lane == e % 32) red[warp][e] = acc[e];
+    __syncthreads();
+    if (live && threadIdx.x < NR * NC) {
+      const int e = threadIdx.x;
+      T tot = 0;
+#pragma unroll
+      for (int w = 0; w < LANES / 32; w++) tot += red[w][e];
+      data[p.dstOff[d] + (e / NC) * (int64_t)p.dstStride[d] + (e % NC)] -= tot;
+    }
+  } else if (live) {
     T* dst = data + p.dstOff[d];
     const int64_t stride = p.dstStride[d];
 #pragma unroll
@@ -359,13 +383,22 @@ template <typename T>
 void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> data) {
   if (plan.numDst == 0) return;
   ProfScope prof(st, KC_ELIM_GATHER, plan.gatherFlops * batch, plan.gatherBytes * sizeof(T) * batch);
-  auto fixed = [&](auto kern, int lanes) {
-    kern<<<dim3(ceilDiv(plan.numDst * lanes, 128), 1, batch), 128, 0, st>>>(plan, data);
-    B200_LAUNCH_CHECK();
+  auto fixed = [&](auto light, auto heavy, int lanes) {
+    if (plan.numLight > 0) {
+      light<<<dim3(ceilDiv(plan.numLight * lanes, 128), 1, batch), 128, 0, st>>>(plan, data, plan.lightList, plan.numLight);
+      B200_LAUNCH_CHECK();
+    }
+    if (plan.numHeavy > 0) {
+      heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), 256, 0, st>>>(plan, data, plan.heavyList, plan.numHeavy);
+      B200_LAUNCH_CHECK();
+    }
   };
-  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) return fixed(elim_gather_fixed_kernel<T, 6, 6, 3, 8>, 8);
-  if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3) return fixed(elim_gather_fixed_kernel<T, 3, 3, 3, 4>, 4);
-  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 6) return fixed(elim_gather_fixed_kernel<T, 6, 6, 6, 8>, 8);
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3)
+    return fixed(elim_gather_fixed_kernel<T, 6, 6, 3, 8>, elim_gather_fixed_kernel<T, 6, 6, 3, 256>, 8);
+  if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
+    return fixed(elim_gather_fixed_kernel<T, 3, 3, 3, 4>, elim_gather_fixed_kernel<T, 3, 3, 3, 256>, 4);
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 6)
+    return fixed(elim_gather_fixed_kernel<T, 6, 6, 6, 8>, elim_gather_fixed_kernel<T, 6, 6, 6, 256>, 8);
   int E = std::min(plan.maxDstElems, 256);
   int64_t threads = plan.numDst * E;
   elim_gather_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(plan, data, E);
