@@ -38,6 +38,8 @@ WORKLOADS = {
                  desc="GRID 120x120 block=6 conn=2 pure supernodal (no sparse elimination), fp64"),
     "flat": dict(kind=0, params=[1000, 0.05], bsize=(3, 3), n_elim=0, auto=True,
                  desc="FLAT size=1000 block=3 fill=0.05, fp64"),
+    "flat_batch": dict(kind=0, params=[2000, 0.03], bsize=(3, 3), n_elim=0, auto=True, batch=64,
+                       desc="batch=64 identical-structure FLAT size=2000 block=3 fill=0.03, batch sharded across the GPUs, fp64"),
     "stress": dict(kind=3, params=[1000000, 200, 2, 3.0, 200, 1.0], bsize=(3, 6), n_elim=1000000, auto=True,
                    desc="sparse-elim stress: 1M independent 3x3 points + 200 cameras, fp64"),
 }
@@ -191,16 +193,44 @@ def run_b200(args):
     s.set_stream(stream)
     we = s.work_estimate()
     flops = we["factor_flops"] + we["solve_flops_per_rhs"]
-    # every rank owns one matrix of the batch: same structure, different values
-    data_h = api.random_data_array(s.data_size, -1, 1, 37 + rank)
-    s.damp(data_h, 0.0, s.order * 1.2)
-    rhs_h = api.random_data_array(s.order, -1, 1, 38 + rank).reshape(1, s.order)
+    batch_total = w.get("batch", 0)
+    if batch_total:
+        # config 4: a fixed batch of identically structured matrices, contiguous shard per rank (strong scaling)
+        from baspacho_b200.sharding import shard_range
+        lo, hi = shard_range(batch_total, rank, world)
+        n_items = hi - lo
+        data_h = np.stack([api.random_data_array(s.data_size, -1, 1, 37 + q) for q in range(lo, hi)]) if n_items else np.zeros((0, s.data_size))
+        for q in range(n_items):
+            s.damp(data_h[q], 0.0, s.order * 1.3)
+        rhs_h = np.stack([api.random_data_array(s.order, -1, 1, 1038 + q).reshape(1, s.order) for q in range(lo, hi)]) if n_items else np.zeros((0, 1, s.order))
+        flops_rank = flops * n_items
+    else:
+        # every rank owns one matrix of the batch: same structure, different values (weak scaling)
+        n_items = 1
+        data_h = api.random_data_array(s.data_size, -1, 1, 37 + rank)
+        s.damp(data_h, 0.0, s.order * 1.2)
+        rhs_h = api.random_data_array(s.order, -1, 1, 38 + rank).reshape(1, s.order)
+        flops_rank = flops
     pin_data = torch.from_numpy(data_h).pin_memory()
     pin_rhs = torch.from_numpy(rhs_h.copy()).pin_memory()
     pristine = pin_data.to(dev)
     work = torch.empty_like(pristine)
     rhs_d = pin_rhs.to(dev)
     x_d = torch.empty_like(rhs_d)
+
+    def do_factor():
+        if batch_total:
+            if n_items:
+                s.factor_batched(work)
+        else:
+            s.factor(work)
+
+    def do_solve():
+        if batch_total:
+            if n_items:
+                s.solve_batched(work, x_d)
+        else:
+            s.solve(work, x_d)
 
     def barrier():
         if world > 1:
@@ -213,9 +243,9 @@ def run_b200(args):
             x_d.copy_(rhs_d, non_blocking=True)
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(stream)
-            s.factor(work)
+            do_factor()
             e1.record(stream)
-            s.solve(work, x_d)
+            do_solve()
             e2.record(stream)
         return e0, e1, e2
 
@@ -241,11 +271,14 @@ def run_b200(args):
     tot_max = float(t.item())
 
     # residual check of the last step (result correctness inside the bench, cheap): ||A x - b|| through addMvFrom
-    y = torch.zeros_like(rhs_d)
-    with torch.cuda.stream(stream):
-        s.add_mv_from(pristine, 0, x_d, y)
-    torch.cuda.synchronize()
-    resid = float((y - rhs_d).norm() / rhs_d.norm())
+    resid = 0.0
+    if n_items:
+        p0, x0, r0 = (pristine[0], x_d[0], rhs_d[0]) if batch_total else (pristine, x_d, rhs_d)
+        y = torch.zeros_like(r0)
+        with torch.cuda.stream(stream):
+            s.add_mv_from(p0, 0, x0, y)
+        torch.cuda.synchronize()
+        resid = float((y - r0).norm() / r0.norm())
 
     # ---- e2e: the C-ABI host-buffer call (pinned host memory in, solution out), H2D + D2H inside the timed region
     x_host = torch.empty_like(pin_rhs).pin_memory()
@@ -254,7 +287,11 @@ def run_b200(args):
         x_host.copy_(pin_rhs)
         barrier()
         t0 = time.perf_counter()
-        s.factor_solve_host(pin_data, x_host, None)
+        if batch_total:
+            for q in range(n_items):  # the host-buffer entry point takes one matrix at a time
+                s.factor_solve_host(pin_data[q], x_host[q], None)
+        else:
+            s.factor_solve_host(pin_data, x_host, None)
         dt = time.perf_counter() - t0
         if it >= 2:
             e2e_times.append(dt)
@@ -306,23 +343,25 @@ def run_b200(args):
                                          find_sparse_elim_ranges=w["auto"])
             d = ocpu.api().random_data_array(o.data_size, -1, 1, 37)
             o.damp(d, 0.0, o.order * 1.2)
-            xr = rhs_h.copy()
+            xr = (rhs_h[0] if batch_total else rhs_h).copy()
             t0 = time.perf_counter()
             o.factor(d)
             o.solve(d, xr)
             dt = time.perf_counter() - t0
             cpu_baseline = {"value": flops / dt / 1e9, "unit": "GF/s", "cores": cores, "kind": "port",
                             "sample": f"full workload, 1 factor+solve ({dt:.2f} s), restated reference BackendFast (OpenBLAS + threads)",
-                            "solution_max_abs_diff_vs_gpu": float(np.abs(xr - x_d.cpu().numpy()).max())}
+                            "solution_max_abs_diff_vs_gpu": None if batch_total else float(np.abs(xr - x_d.cpu().numpy()).max())}
         except Exception as e:  # the baseline must never take the GPU number down
             cpu_baseline = {"value": None, "unit": "GF/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
-    value = world * args.steps * flops / tot_max / 1e9
+    total_flops = flops * batch_total if batch_total else world * flops
+    value = args.steps * total_flops / tot_max / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": tot_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": tot_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if batch_total else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"] + (f"; batch of {world} such matrices sharded 1 per GPU" if world > 1 else ""),
+        "config": {"workload": w["desc"] + (f"; batch of {world} such matrices sharded 1 per GPU" if world > 1 and not batch_total else ""),
+                   "batch": batch_total or world, "items_on_rank0": n_items,
                    "order": s.order, "data_size": s.data_size, "nnz_l": we["nnz_l"], "factor_gflop": we["factor_flops"] / 1e9,
                    "solve_gflop": we["solve_flops_per_rhs"] / 1e9, "n_rhs": 1, "lumps": s.num_lumps,
                    "dense_lump_sizes": np.diff(s.lumpStart[w["n_elim"]:]).tolist()[-8:] if w["n_elim"] else None,
@@ -333,7 +372,7 @@ def run_b200(args):
         "factor_gfs": we["factor_flops"] / (np.mean(fac_ms) * 1e-3) / 1e9,
         "residual": resid, "wall_s_timed_region": t_wall,
         "gpu_launches": launches,
-        "e2e": {"value": world * flops / e2e_s / 1e9, "unit": "GF/s", "ms_per_step": e2e_s * 1e3,
+        "e2e": {"value": total_flops / e2e_s / 1e9, "unit": "GF/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(pin_data.numel() * 8 + pin_rhs.numel() * 8),
                 "d2h_bytes_per_step": int(pin_rhs.numel() * 8),
                 "api": "bspb200_factor_solve_host (C ABI, pinned host buffers)"},
