@@ -278,7 +278,7 @@ __device__ __forceinline__ Vec2<float> load2(const float* p) {
 }
 
 template <typename T, bool DO_POTRF>
-__global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
+__global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
                                                              Operand<T> Bop, int64_t ldb) {
   constexpr int NW = kPanelThreads / 32;  // 8 warps
   constexpr int G = kPanelG, R = kPanelRows, W = 32 / G;
@@ -313,51 +313,101 @@ __global__ void __launch_bounds__(kPanelThreads) panel_kernel(int n, int64_t row
         }
     }
     __syncthreads();
-    T* colbuf = Xs;
+    T* colbuf = Xs;                // [4][kNB]  raw (not yet scaled) columns of the current 4-column group
+    T* ybuf = Xs + 4 * kNB;        // [kNB][4]  finished rows of the group: L[i][j0 .. j0+3]
     T reg[RA][CU];
 #pragma unroll
     for (int a = 0; a < RA; a++)
 #pragma unroll
       for (int u = 0; u < CU; u++) reg[a][u] = S[(lane + 32 * a) * kLDS + warp + NW * u];
+    // Four columns per step (two barriers per step): the owners publish the raw columns, every thread factors the
+    // 4x4 pivot block redundantly in registers and solves its own rows against it, three warps publish the finished
+    // rows, then the rank-4 update of the trailing register tiles runs with all operands loaded up front.
 #pragma unroll
     for (int u = 0; u < CU; u++) {
-      for (int w = 0; w < NW; w++) {
-        const int j = NW * u + w;
-        if (j >= n) break;
-        T* cb = colbuf + (j & 1) * kNB;
-        if (warp == w) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j0 = NW * u + 4 * h;
+        if (j0 < n) {
+          const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (lane + 32 * a >= j0) colbuf[q * kNB + lane + 32 * a] = reg[a][u];
+          }
+          __syncthreads();
+          // pivot block d[r][c] = entry (j0 + r, j0 + c), r >= c; columns beyond n act as identity
+          T d[4][4], raw[RA][4];
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = c; r < 4; r++) d[r][c] = colbuf[c * kNB + j0 + r];
 #pragma unroll
           for (int a = 0; a < RA; a++)
-            if (lane + 32 * a >= j) cb[lane + 32 * a] = reg[a][u];
-        }
-        __syncthreads();
-        // operands of the rank-1 update: all shared loads issued before any use. Entries above the diagonal of the
-        // register tile are never read, so the update needs no (row >= column) predicate; finished rows get li = 0.
-        T scv[CU], li[RA];
 #pragma unroll
-        for (int u2 = u; u2 < CU; u2++) scv[u2] = cb[warp + NW * u2];
+            for (int c = 0; c < 4; c++) raw[a][c] = colbuf[c * kNB + lane + 32 * a];
 #pragma unroll
-        for (int a = 0; a < RA; a++) li[a] = cb[lane + 32 * a];
-        const T piv = cb[j];
-        const T rs = rsqrt(piv);
-        const T invp = rs * rs;
+          for (int c = 0; c < 4; c++)
+            if (j0 + c >= n) d[c][c] = T(1);
+          T rs[4];
 #pragma unroll
-        for (int a = 0; a < RA; a++) li[a] = (lane + 32 * a > j) ? li[a] * invp : T(0);
-        if (warp <= w) scv[u] = T(0);  // columns <= j of this slot are finished (or the pivot column itself)
+          for (int c = 0; c < 4; c++) {
 #pragma unroll
-        for (int a = 0; a < RA; a++) {
-          if (j < 32 * a + 31) {  // some row of the slot is still active (warp uniform)
+            for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
+            rs[c] = rsqrt(d[c][c]);
 #pragma unroll
-            for (int u2 = u; u2 < CU; u2++)
-              if (NW * u2 <= 32 * a + 31) reg[a][u2] -= li[a] * scv[u2];  // static: the tile touches the lower triangle
+            for (int r = c + 1; r < 4; r++) {
+#pragma unroll
+              for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
+              d[r][c] *= rs[c];
+            }
           }
-        }
-        if (warp == w) {
+          // own rows: y = raw * D^-T (entries above the diagonal of the pivot block and finished rows -> 0)
+          T y[RA][4];
 #pragma unroll
           for (int a = 0; a < RA; a++) {
-            const int i = lane + 32 * a;
-            if (i == j) reg[a][u] = piv * rs;
-            else if (i > j) reg[a][u] *= rs;
+            const int t = lane + 32 * a - j0;  // row index relative to the group
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              T v = raw[a][c];
+#pragma unroll
+              for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
+              y[a][c] = (t >= c) ? v * rs[c] : T(0);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (warp == a) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
+            }
+          __syncthreads();
+          // rank-4 update of the columns after the group
+          T yc[CU][4];
+#pragma unroll
+          for (int u2 = u; u2 < CU; u2++) {
+            const Vec2<T> lo = load2(ybuf + (warp + NW * u2) * 4), hi = load2(ybuf + (warp + NW * u2) * 4 + 2);
+            yc[u2][0] = lo.v[0], yc[u2][1] = lo.v[1], yc[u2][2] = hi.v[0], yc[u2][3] = hi.v[1];
+          }
+          if (!(h == 0 && warp >= 4)) {  // this slot's column is inside (or before) the group: no update
+#pragma unroll
+            for (int c = 0; c < 4; c++) yc[u][c] = T(0);
+          }
+#pragma unroll
+          for (int a = 0; a < RA; a++) {
+            if (j0 + 3 < 32 * a + 31) {  // some row of the slot is below the group (warp uniform)
+#pragma unroll
+              for (int u2 = u; u2 < CU; u2++)
+                if (NW * u2 <= 32 * a + 31) {  // static: the tile touches the lower triangle
+#pragma unroll
+                  for (int c = 0; c < 4; c++) reg[a][u2] -= y[a][c] * yc[u2][c];
+                }
+            }
+          }
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (lane + 32 * a >= j0) reg[a][u] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
           }
         }
       }
@@ -589,6 +639,33 @@ static void potrfTrsmPanel(cudaStream_t st, int batch, int n, int64_t rows, Oper
   launchPanel<T, true>(st, batch, n, rows, L, ldl, B, ldb);
 }
 
+// side stream + events of the lookahead schedule (one per process; a Solver is driven by one host thread)
+struct Lookahead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t evPanel = nullptr, evPart2 = nullptr, evStart = nullptr, evDone = nullptr;
+};
+static Lookahead& lookahead() {
+  static Lookahead la = [] {
+    Lookahead l;
+    int lo = 0, hi = 0;
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200_CUDA(cudaStreamCreateWithPriority(&l.side, cudaStreamNonBlocking, hi));  // greatest priority
+    B200_CUDA(cudaEventCreateWithFlags(&l.evStart, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&l.evDone, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&l.evPanel, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&l.evPart2, cudaEventDisableTiming));
+    return l;
+  }();
+  return la;
+}
+static int& lookaheadMode() {
+  static int mode = [] {
+    const char* e = getenv("BSPB200_LOOKAHEAD");
+    return e ? atoi(e) : 1;
+  }();
+  return mode;
+}
+
 // Recursive blocked Cholesky of the (n + rowsBelow) x n trapezoid (row-major, ld). Columns [c0, c0 + w):
 //   w small  : potrfBlock on the diagonal block + trsmBlock on every row below it
 //   otherwise: left half; trailing update of the right half (lower-only GEMM, K = left width); right half
@@ -630,7 +707,42 @@ static void potrfRec(cudaStream_t st, int batch, int64_t totalRows, int64_t c0, 
 template <typename T>
 void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld) {
   if (n <= 0) return;
-  potrfRec<T>(st, batch, n + rowsBelow, 0, n, A, ld);
+  if (lookaheadMode() == 0 || n <= 2 * kNB) {
+    potrfRec<T>(st, batch, n + rowsBelow, 0, n, A, ld);
+    return;
+  }
+  // Right-looking over 96-column panels with a depth-1 lookahead: the trailing update of panel k is split into
+  //   part 1 = block column k+1 (what panel k+1 needs), on the caller's stream, and
+  //   part 2 = every later column, on a low-priority side stream,
+  // so the latency-bound panel k+1 (diagonal Cholesky + triangular solve) runs while part 2 of panel k keeps the
+  // tensor pipes busy. Dependencies: part2(k) waits for panel(k) (event); part1(k+1) waits for part2(k) (event).
+  Lookahead& la = lookahead();
+  const int64_t total = n + rowsBelow, nb = kNB;
+  cudaStream_t crit = la.side;  // high priority: panels + part 1 (the critical path); part 2 stays on the caller's stream
+  B200_CUDA(cudaEventRecord(la.evStart, st));
+  B200_CUDA(cudaStreamWaitEvent(crit, la.evStart, 0));
+  bool pendingP2 = false;
+  for (int64_t j0 = 0; j0 < n; j0 += nb) {
+    const int64_t jb = std::min<int64_t>(nb, n - j0), r0 = j0 + jb;
+    Operand<T> diag = shifted(A, j0 * ld + j0);
+    potrfTrsmPanel<T>(crit, batch, (int)jb, total - r0, diag, ld, shifted(A, r0 * ld + j0), ld);
+    if (r0 >= n) break;
+    const int64_t jb2 = std::min<int64_t>(nb, n - r0), r1 = r0 + jb2;
+    if (r1 < n) B200_CUDA(cudaEventRecord(la.evPanel, crit));
+    if (pendingP2) B200_CUDA(cudaStreamWaitEvent(crit, la.evPart2, 0));
+    Operand<T> P = shifted(A, r0 * ld + j0);
+    gemmNT<T>(crit, batch, total - r0, jb2, jb, T(-1), P, ld, P, ld, T(1), shifted(A, r0 * ld + r0), ld, true);
+    pendingP2 = false;
+    if (r1 < n) {
+      B200_CUDA(cudaStreamWaitEvent(st, la.evPanel, 0));
+      Operand<T> P2 = shifted(A, r1 * ld + j0);
+      gemmNT<T>(st, batch, total - r1, n - r1, jb, T(-1), P2, ld, P2, ld, T(1), shifted(A, r1 * ld + r1), ld, true);
+      B200_CUDA(cudaEventRecord(la.evPart2, st));
+      pendingP2 = true;
+    }
+  }
+  B200_CUDA(cudaEventRecord(la.evDone, crit));
+  B200_CUDA(cudaStreamWaitEvent(st, la.evDone, 0));
 }
 
 template <typename T>
