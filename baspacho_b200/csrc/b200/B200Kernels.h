@@ -59,6 +59,19 @@ void trsmBlock(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, in
 template <typename T>
 void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld);
 
+// diagonal Cholesky + triangular solve of many small lump columns in one launch (work list on the device)
+struct WavePanel;
+template <typename T>
+void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const WavePanel* work, int64_t count, double flops);
+
+// wavefront update of the small target lumps of one level (WaveKernels.cu)
+struct WaveTile;
+struct WaveTarget;
+struct WaveSource;
+template <typename T>
+void waveUpdate(cudaStream_t st, int batch, Operand<T> data, const WaveTile* tiles, int64_t count,
+                const WaveTarget* targets, const WaveSource* sources, const int32_t* rowMap);
+
 // X * tril(L)^T = B for any n (blocked): L n x n (ldl), B rows x n (ldb)
 template <typename T>
 void trsmAny(cudaStream_t st, int batch, int64_t n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B, int64_t ldb);

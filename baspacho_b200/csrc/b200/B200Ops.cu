@@ -15,6 +15,7 @@
 #include "B200Kernels.h"
 #include "B200Plan.h"
 #include "B200Sparse.h"
+#include "B200Wave.h"
 
 namespace BaSpaCho {
 namespace {
@@ -65,6 +66,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     dsk.boardRowLump = dBoardRowLump.ptr(), dsk.boardChainColOrd = dBoardChainColOrd.ptr();
     dsk.numSpans = s.numSpans(), dsk.numLumps = s.numLumps();
     spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
+    if (const char* e = getenv("BSPB200_WAVEFRONT")) useWavefront = atoi(e) != 0;
     // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
     potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
     solveSparseLStat.enabled = solveSparseLtStat.enabled = pseudoFactorStat.enabled = symmStat.enabled = false;
@@ -131,8 +133,46 @@ struct B200SymbolicCtx : SymbolicCtx {
     return scratchBytes.ptr();
   }
 
+  // wavefront plan of the dense lumps (built at the first full factorization, reused afterwards)
+  struct DevWave {
+    WavePlan host;  // levels + counts stay on the host; the big arrays are released after upload
+    DevBuf<WaveTarget> targets;
+    DevBuf<WaveSource> sources;
+    DevBuf<int32_t> rowMap;
+    DevBuf<WaveTile> tiles;
+    DevBuf<WavePanel> panels;
+    vector<double> panelFlops;  // per level
+  };
+  std::unique_ptr<DevWave> wave;
+  const DevWave& wavePlan(int64_t firstLump) {
+    if (!wave || wave->host.firstLump != firstLump) {
+      auto w = std::make_unique<DevWave>();
+      w->host = buildWavePlan(skel, firstLump);
+      WavePlan& p = w->host;
+      for (const WaveLevel& L : p.levels) {
+        double f = 0;
+        for (int32_t i = L.panelBegin; i < L.panelEnd; i++)
+          if (p.panels[i].slab == 0) {
+            double n = p.panels[i].n, r = p.panels[i].rows;
+            f += n * n * n / 3 + r * n * n;
+          }
+        w->panelFlops.push_back(f);
+      }
+      w->targets.upload(p.targets), w->sources.upload(p.sources), w->rowMap.upload(p.rowMap);
+      w->tiles.upload(p.tiles), w->panels.upload(p.panels);
+      vector<WaveTarget>().swap(p.targets);
+      vector<WaveSource>().swap(p.sources);
+      vector<int32_t>().swap(p.rowMap);
+      vector<WaveTile>().swap(p.tiles);
+      vector<WavePanel>().swap(p.panels);
+      wave = std::move(w);
+    }
+    return *wave;
+  }
+
   const CoalescedBlockMatrixSkel& skel;
   cudaStream_t stream = nullptr;
+  bool useWavefront = true;
   vector<const B200SymElimCtx*> elimRegistry;  // elimination ranges in the order the Solver prepared them
   DevSkel dsk;
   DevBuf<int64_t> dSpanStart, dSpanToLump, dLumpStart, dLumpToSpan, dSpanOffsetInLump, dChainColPtr, dChainRowSpan,
@@ -264,32 +304,55 @@ struct B200NumericCtx : NumericCtx<TT> {
       elimGather<T>(sym.stream, m.batch, e->dev, m);
     }
     const int64_t firstSrc = std::max(startLump, denseFrom);
-    for (int64_t l = firstSrc; l < skel.numLumps(); l++) {
-      bool prepared = false;
-      for (int64_t r = skel.boardRowPtr[l], rEnd = skel.boardRowPtr[l + 1] - 1; r < rEnd; r++) {
-        const int64_t src = skel.boardColLump[r];
-        if (src >= upToLump) break;
-        if (src < firstSrc) continue;
-        if (!prepared) prepareAssemble(l), prepared = true;
-        const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
-        const int64_t k = skel.lumpSize(src);
-        const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
-        const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
-        const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
-        const int64_t rowsInBoard = skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin;
-        const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
-        BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
-        Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
-        gemmNT<T>(sym.stream, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(temp(), 0), rowsInBoard,
-                  false);
-        b200::assemble<T>(sym.stream, m.batch, sym.dsk, sym.spanToChainOffset.ptr(), m, temp(), rowBegin,
-                          skel.lumpSize(l), cb + ch0, rowsInBoard, chEnd - ch0, ch1 - ch0, rowsToEnd);
+    if (sym.useWavefront && firstSrc == denseFrom && upToLump == skel.numLumps() && firstSrc < skel.numLumps()) {
+      // level-of-tree wavefront: per level one gather-GEMM launch + one batched panel launch for the small lumps,
+      // the per-lump path for the wide ones
+      const auto& wv = sym.wavePlan(firstSrc);
+      Operand<T> all = opnd(m, 0);
+      for (size_t lv = 0; lv < wv.host.levels.size(); lv++) {
+        const WaveLevel& L = wv.host.levels[lv];
+        waveUpdate<T>(sym.stream, m.batch, all, wv.tiles.ptr() + L.tileBegin, L.tileEnd - L.tileBegin,
+                      wv.targets.ptr(), wv.sources.ptr(), wv.rowMap.ptr());
+        for (int64_t l : L.bigLumps) updateLump(m, l, firstSrc, upToLump);
+        potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
+                               wv.panelFlops[lv]);
+        for (int64_t l : L.bigLumps) factorLumpColumn(m, l);
       }
-      if (l < upToLump) {
-        const int64_t n = skel.lumpSize(l);
-        potrfTrapezoid<T>(sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
-      }
+      return;
     }
+    for (int64_t l = firstSrc; l < skel.numLumps(); l++) {
+      updateLump(m, l, firstSrc, upToLump);
+      if (l < upToLump) factorLumpColumn(m, l);
+    }
+  }
+
+  // contributions of the already factored sources [firstSrc, min(l, upToLump)) into lump l: GEMM into the temp + scatter
+  void updateLump(const Mats<T>& m, int64_t l, int64_t firstSrc, int64_t upToLump) {
+    bool prepared = false;
+    for (int64_t r = skel.boardRowPtr[l], rEnd = skel.boardRowPtr[l + 1] - 1; r < rEnd; r++) {
+      const int64_t src = skel.boardColLump[r];
+      if (src >= upToLump) break;
+      if (src < firstSrc) continue;
+      if (!prepared) prepareAssemble(l), prepared = true;
+      const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
+      const int64_t k = skel.lumpSize(src);
+      const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
+      const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
+      const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
+      const int64_t rowsInBoard = skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin;
+      const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
+      BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
+      Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
+      gemmNT<T>(sym.stream, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(temp(), 0), rowsInBoard,
+                false);
+      b200::assemble<T>(sym.stream, m.batch, sym.dsk, sym.spanToChainOffset.ptr(), m, temp(), rowBegin,
+                        skel.lumpSize(l), cb + ch0, rowsInBoard, chEnd - ch0, ch1 - ch0, rowsToEnd);
+    }
+  }
+
+  void factorLumpColumn(const Mats<T>& m, int64_t l) {
+    const int64_t n = skel.lumpSize(l);
+    potrfTrapezoid<T>(sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
   }
 
   B200SymbolicCtx& sym;

@@ -9,6 +9,7 @@
 //   trsmAny        - blocked X L^T = B for any size
 #include <algorithm>
 #include "B200Kernels.h"
+#include "B200Wave.h"
 
 namespace BaSpaCho {
 namespace b200 {
@@ -279,7 +280,7 @@ __device__ __forceinline__ Vec2<float> load2(const float* p) {
 
 template <typename T, bool DO_POTRF>
 __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
-                                                             Operand<T> Bop, int64_t ldb) {
+                                                             Operand<T> Bop, int64_t ldb, const WavePanel* work) {
   constexpr int NW = kPanelThreads / 32;  // 8 warps
   constexpr int G = kPanelG, R = kPanelRows, W = 32 / G;
   constexpr int LA = kNB / NW, LU = kNB / 32;
@@ -288,6 +289,15 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
   T* invd = Lt + kNB * kLDT;              // [kNB]
   T* Xs = invd + kNB;                     // [R][kLDX]  (also the 2 x kNB column buffer of the Cholesky phase)
   T* __restrict__ L = Lop.at(blockIdx.z);
+  T* __restrict__ B = Bop.at(blockIdx.z);
+  int slab = blockIdx.x;
+  if (work) {  // batched over a work list (wavefront): one item = (lump column, 64-row slab)
+    const WavePanel w = work[blockIdx.x];
+    n = w.n, rows = w.rows, slab = w.slab;
+    L += w.dataOff;
+    B = L + (int64_t)n * n;
+    ldl = ldb = n;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (DO_POTRF) {
@@ -422,7 +432,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
         const int i = lane + 32 * a, c = warp + NW * u;
         if (c <= i && i < n) {
           Lt[c * kLDT + ltPos(i)] = reg[a][u];
-          if (blockIdx.x == 0) L[(int64_t)i * ldl + c] = reg[a][u];
+          if (slab == 0) L[(int64_t)i * ldl + c] = reg[a][u];
         }
       }
   } else {
@@ -441,8 +451,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
   __syncthreads();
   if (tid < n) invd[tid] = T(1) / Lt[tid * kLDT + ltPos(tid)];
 
-  T* __restrict__ B = Bop.at(blockIdx.z);
-  const int64_t r0 = (int64_t)blockIdx.x * R;
+  const int64_t r0 = (int64_t)slab * R;
   const int nr = (int)min((int64_t)R, rows - r0);
   {  // row slab -> smem, all loads in flight at once
     constexpr int RW = R / NW;
@@ -613,9 +622,25 @@ static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand
   static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
   (void)once;
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
-  panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb);
+  panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr);
   B200_LAUNCH_CHECK();
 }
+
+// batched over a device work list (one CTA per (lump, slab) item): the small supernodes of one tree level
+template <typename T>
+void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const WavePanel* work, int64_t count,
+                         double flops) {
+  if (count <= 0) return;
+  static_assert(WavePlan::kPanelRows == kPanelRows, "slab size of the plan and of the kernel differ");
+  size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
+  static bool once = (setSmem(panel_kernel<T, true>, smem), true);
+  (void)once;
+  ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
+  panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(0, 0, data, 0, data, 0, work);
+  B200_LAUNCH_CHECK();
+}
+template void potrfTrsmPanelBatch<double>(cudaStream_t, int, Operand<double>, const WavePanel*, int64_t, double);
+template void potrfTrsmPanelBatch<float>(cudaStream_t, int, Operand<float>, const WavePanel*, int64_t, double);
 
 template <typename T>
 void potrfBlock(cudaStream_t st, int batch, int n, Operand<T> A, int64_t lda) {
