@@ -81,7 +81,9 @@ void trsmAny(cudaStream_t st, int batch, int64_t n, int64_t rows, Operand<T> L, 
 // tril(L) X = C (transposed=false) or tril(L)^T X = C (transposed=true), L n x n row-major (ldl), any n
 template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
-             bool transposed, Operand<T> scratch /* n x nRHS per batch item, used when n > one block */);
+             bool transposed, Operand<T> scratch /* n x nRHS per batch item, used when n > one block */,
+             Operand<T> invScratch /* optional: 2 x 96 x 96 x ceil(n / 96) per batch item -> inverse-based block steps */,
+             bool inversesReady = false /* the scratch already holds the inverses of this matrix */);
 
 // out[i * outRowStride + c * outColStride] (+)= alpha * sum_q M[i][q] * X[c * ldx + q]   (M rows x cols, ldm)
 // (tmp row-major rows x nRHS: strides (nRHS, 1); a column-major vector: strides (1, ld))

@@ -67,6 +67,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     dsk.numSpans = s.numSpans(), dsk.numLumps = s.numLumps();
     spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
     if (const char* e = getenv("BSPB200_WAVEFRONT")) useWavefront = atoi(e) != 0;
+    if (const char* e = getenv("BSPB200_INVERSE_SOLVE")) useInverseSolve = atoi(e) != 0;
     // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
     potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
     solveSparseLStat.enabled = solveSparseLtStat.enabled = pseudoFactorStat.enabled = symmStat.enabled = false;
@@ -173,6 +174,7 @@ struct B200SymbolicCtx : SymbolicCtx {
   const CoalescedBlockMatrixSkel& skel;
   cudaStream_t stream = nullptr;
   bool useWavefront = true;
+  bool useInverseSolve = true;
   vector<const B200SymElimCtx*> elimRegistry;  // elimination ranges in the order the Solver prepared them
   DevSkel dsk;
   DevBuf<int64_t> dSpanStart, dSpanToLump, dLumpStart, dLumpToSpan, dSpanOffsetInLump, dChainColPtr, dChainRowSpan,
@@ -370,13 +372,42 @@ struct B200SolveCtx : SolveCtx<TT> {
     tlsSyncStream = sym.stream;
   }
 
-  // two scratch vectors of order x nRHS per batch item: [0] the gemv/assembleVec temp of the reference's solve ctx,
-  // [1] the solved-block staging of the blocked dense triangular solve
+  // scratch per batch item: [0] the gemv/assembleVec temp of the reference's solve ctx (order x nRHS), [1] the
+  // solved-block staging of the blocked dense triangular solve (order x nRHS), [2] the inverses of the 96 x 96
+  // diagonal blocks of the widest lump (2 x 96 x 96 per block)
+  int64_t vecStride() const { return std::max<int64_t>(1, skel.order() * nRHS); }
+  int64_t invStride() const {
+    int64_t widest = 0;
+    for (int64_t l = 0; l < skel.numLumps(); l++) widest = std::max(widest, skel.lumpSize(l));
+    return widest > 96 ? 2 * 96 * 96 * ((widest + 95) / 96) : 0;
+  }
+  T* scratchBase() {
+    if (invStrideCache < 0) invStrideCache = invStride();
+    return (T*)sym.scratch((size_t)(2 * vecStride() + invStrideCache) * batch * sizeof(T));
+  }
   Work<T> temp(int which = 0) {
     Work<T> w;
-    w.stride = std::max<int64_t>(1, skel.order() * nRHS);
-    w.base = (T*)sym.scratch((size_t)w.stride * batch * sizeof(T) * 2) + (size_t)which * w.stride * batch;
+    w.stride = vecStride();
+    w.base = scratchBase() + (size_t)which * w.stride * batch;
     return w;
+  }
+  Operand<T> invScratch() {
+    Operand<T> o;
+    if (invStrideCache < 0) invStrideCache = invStride();
+    if (invStrideCache == 0 || !sym.useInverseSolve) return o;
+    o.base = scratchBase() + (size_t)2 * vecStride() * batch;
+    o.bstride = invStrideCache;
+    return o;
+  }
+  int64_t invStrideCache = -1;
+  // the block inverses in the scratch belong to (matrix, offset, n) of the last wide lump solved through this context
+  // (solve() runs solveL then solveLt on the same factor: the second pass reuses them)
+  const void* invData = nullptr;
+  int64_t invOff = -1, invN = -1;
+  bool invReady(const TT* data, int64_t offM, int64_t n) {
+    bool same = invData == (const void*)data && invOff == offM && invN == n;
+    invData = data, invOff = offM, invN = n;
+    return same && n > 96;
   }
   Work<T> temp2() { return temp(1); }
 
@@ -412,13 +443,13 @@ struct B200SolveCtx : SolveCtx<TT> {
   void solveL(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0));
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), invScratch(), invReady(data, offM, n));
   }
 
   void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLtStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0));
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), invScratch(), invReady(data, offM, n));
   }
 
   void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,

@@ -232,10 +232,62 @@ void symmLower(cudaStream_t st, int batch, int64_t n, T alpha, Operand<T> M, Ope
 //   backward: y[col] -= L[block, col]^T . x_block    for 128 columns before the block per CTA (thread per column)
 // The solved block goes to a scratch vector (the input block must stay intact for the other CTAs).
 constexpr int kStepRows = 64, kStepCols = 128;
+// the CTA's share of the update with the solved block xs (see solve_step_kernel)
+template <typename T, bool TR>
+__device__ __forceinline__ void stepUpdate(int64_t n, int64_t j0, int jb, const T* __restrict__ L, int64_t ldl, T* C,
+                                           int64_t ldc, const T* xs, int g0, int ng) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!TR) {
+      const int64_t rbeg = j0 + jb + (int64_t)blockIdx.x * kStepRows;
+      constexpr int RPW = kStepRows / kTrsvWarps;  // rows per warp
+      constexpr int RB = 8;                        // rows in flight per warp
+      for (int rr0 = 0; rr0 < RPW; rr0 += RB) {
+        const int64_t rowBase = rbeg + warp * RPW + rr0;
+        if (rowBase >= n) break;
+        T mv[RB][3];
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++)
+#pragma unroll
+          for (int u = 0; u < 3; u++)
+            mv[rr][u] = (rowBase + rr < n && lane + 32 * u < jb) ? L[(rowBase + rr) * ldl + j0 + lane + 32 * u] : T(0);
+        for (int q = 0; q < ng; q++) {
+          const T x0 = xs[q * kTB + lane], x1 = xs[q * kTB + lane + 32], x2 = xs[q * kTB + lane + 64];
+          T v[RB];
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++) v[rr] = mv[rr][0] * x0 + mv[rr][1] * x1 + mv[rr][2] * x2;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) v[rr] += __shfl_xor_sync(0xffffffffu, v[rr], o);
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++)
+            if (lane == rr && rowBase + rr < n) C[(int64_t)(g0 + q) * ldc + rowBase + rr] -= v[rr];
+        }
+      }
+    } else {
+      const int64_t col = (int64_t)blockIdx.x * kStepCols + tid;
+      if (col < j0) {
+        T acc[kTrsvWarps];
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++) acc[q] = T(0);
+        const T* m = L + j0 * ldl + col;
+#pragma unroll 8
+        for (int r = 0; r < jb; r++) {
+          const T mv = m[(int64_t)r * ldl];
+#pragma unroll
+          for (int q = 0; q < kTrsvWarps; q++) acc[q] += mv * xs[q * kTB + r];
+        }
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++)
+          if (q < ng) C[(int64_t)(g0 + q) * ldc + col] -= acc[q];
+      }
+    }
+}
+
 template <typename T, bool TR>
 __global__ void __launch_bounds__(kTrsvWarps * 32)
     solve_step_kernel(int64_t n, int64_t j0, int jb, Operand<T> Lop, int64_t ldl, Operand<T> Cop, int64_t ldc,
-                      Operand<T> Xop, int64_t ldx, int nRHS) {
+                      Operand<T> Xop, int64_t ldx, int nRHS, Operand<T> Wop, bool useInv) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   T* Ls = reinterpret_cast<T*>(smemRaw);
   T* invd = Ls + kTB * kTLD;
@@ -244,6 +296,40 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
   T* C = Cop.at(blockIdx.z);
   T* X = Xop.at(blockIdx.z);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (useInv) {
+    // diagonal block solve = product with the precomputed inverse of the block (no serial column chain):
+    // forward x = W b reads W^T, backward x = W^T b reads W, both coalesced over the output index
+    const T* __restrict__ Wm = Wop.at(blockIdx.z) + (j0 / kTB) * (int64_t)(2 * kTB * kTB) + (TR ? 0 : kTB * kTB);
+    T* bs = Ls;  // [kTrsvWarps][kTB] right-hand sides of the group
+    for (int g0 = 0; g0 < nRHS; g0 += kTrsvWarps) {
+      const int ng = min(kTrsvWarps, nRHS - g0);
+      for (int i = tid; i < kTrsvWarps * kTB; i += kTrsvWarps * 32) {
+        const int q = i / kTB, r = i % kTB;
+        bs[i] = (q < ng && r < jb) ? C[(int64_t)(g0 + q) * ldc + j0 + r] : T(0);
+      }
+      __syncthreads();
+      if (tid < kTB) {
+        T acc[kTrsvWarps];
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++) acc[q] = T(0);
+#pragma unroll 8
+        for (int r = 0; r < kTB; r++) {
+          const T wv = Wm[r * kTB + tid];
+#pragma unroll
+          for (int q = 0; q < kTrsvWarps; q++) acc[q] += wv * bs[q * kTB + r];
+        }
+#pragma unroll
+        for (int q = 0; q < kTrsvWarps; q++) {
+          xs[q * kTB + tid] = acc[q];
+          if (blockIdx.x == 0 && q < ng && tid < jb) X[(int64_t)(g0 + q) * ldx + j0 + tid] = acc[q];
+        }
+      }
+      __syncthreads();
+      stepUpdate<T, TR>(n, j0, jb, L, ldl, C, ldc, xs, g0, ng);
+      __syncthreads();
+    }
+    return;
+  }
   for (int i = tid; i < kTB * kTLD + kTB; i += kTrsvWarps * 32) Ls[i] = T(0);  // zero padding (block < 96, invd)
   __syncthreads();
   {
@@ -320,52 +406,182 @@ __global__ void __launch_bounds__(kTrsvWarps * 32)
     }
     __syncthreads();
     const int ng = min(kTrsvWarps, nRHS - g0);
+    stepUpdate<T, TR>(n, j0, jb, L, ldl, C, ldc, xs, g0, ng);
+    __syncthreads();
+  }
+}
+
+// Inverse-based block step, latency optimised: every global operand of the step (the block inverse, the CTA's slice
+// of the factor panel, the right-hand-side block) is requested up front and held in registers, so a step costs about
+// one memory latency + two barriers instead of a chain of dependent loads.
+//   forward : CTA = 64 rows below the block (warp = 8 rows, lanes over the 96 block columns)
+//   backward: CTA = 128 columns before the block (thread = column, two halves of the 96 block rows)
+constexpr int kInvThreads = 256, kInvWarps = 8, kInvRHS = 4;
+template <typename T, bool TR>
+__global__ void __launch_bounds__(kInvThreads, 1)
+    solve_step_inv_kernel(int64_t n, int64_t j0, int jb, Operand<T> Lop, int64_t ldl, Operand<T> Cop, int64_t ldc,
+                          Operand<T> Xop, int64_t ldx, int nRHS, Operand<T> Wop) {
+  __shared__ T bs[kInvRHS][kTB];             // right-hand sides of the block
+  __shared__ T part[kInvWarps][kInvRHS][kTB];  // partial products per warp / per half
+  __shared__ T xs[kInvRHS][kTB];             // solved block
+  const T* __restrict__ L = Lop.at(blockIdx.z);
+  T* C = Cop.at(blockIdx.z);
+  T* X = Xop.at(blockIdx.z);
+  const T* __restrict__ Wm = Wop.at(blockIdx.z) + (j0 / kTB) * (int64_t)(2 * kTB * kTB) + (TR ? 0 : kTB * kTB);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- all loads of the step, issued back to back
+  constexpr int RW = kTB / kInvWarps;  // 12 rows of the inverse per warp
+  T wv[RW][3];
+#pragma unroll
+  for (int a = 0; a < RW; a++)
+#pragma unroll
+    for (int u = 0; u < 3; u++) wv[a][u] = Wm[(warp * RW + a) * kTB + lane + 32 * u];
+  constexpr int UF = kStepRows / kInvWarps;  // forward: 8 rows per warp
+  constexpr int UB = kTB / 2;               // backward: 48 block rows per half
+  T mv[TR ? UB : UF * 3];
+  const int64_t rowBase = j0 + jb + (int64_t)blockIdx.x * kStepRows + warp * UF;  // forward
+  const int64_t col = (int64_t)blockIdx.x * kStepCols + (tid & (kStepCols - 1));    // backward
+  const int half = tid / kStepCols;
+  if (!TR) {
+#pragma unroll
+    for (int rr = 0; rr < UF; rr++)
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+        mv[rr * 3 + u] = (rowBase + rr < n && lane + 32 * u < jb) ? L[(rowBase + rr) * ldl + j0 + lane + 32 * u] : T(0);
+  } else {
+#pragma unroll
+    for (int r = 0; r < UB; r++) {
+      const int br = half * UB + r;
+      mv[r] = (col < j0 && br < jb) ? L[(j0 + br) * ldl + col] : T(0);
+    }
+  }
+
+  for (int g0 = 0; g0 < nRHS; g0 += kInvRHS) {
+    const int ng = min(kInvRHS, nRHS - g0);
+    for (int i = tid; i < kInvRHS * kTB; i += kInvThreads) {
+      const int q = i / kTB, r = i % kTB;
+      bs[q][r] = (q < ng && r < jb) ? C[(int64_t)(g0 + q) * ldc + j0 + r] : T(0);
+    }
+    __syncthreads();
+    // x = W b: every warp covers 12 rows of the sum, lanes cover the outputs
+#pragma unroll
+    for (int q = 0; q < kInvRHS; q++) {
+      T a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int a = 0; a < RW; a++) {
+        const T b = bs[q][warp * RW + a];
+        a0 += wv[a][0] * b, a1 += wv[a][1] * b, a2 += wv[a][2] * b;
+      }
+      part[warp][q][lane] = a0, part[warp][q][lane + 32] = a1, part[warp][q][lane + 64] = a2;
+    }
+    __syncthreads();
+    for (int i = tid; i < kInvRHS * kTB; i += kInvThreads) {
+      const int q = i / kTB, r = i % kTB;
+      T v = 0;
+#pragma unroll
+      for (int w = 0; w < kInvWarps; w++) v += part[w][q][r];
+      xs[q][r] = v;
+      if (blockIdx.x == 0 && q < ng && r < jb) X[(int64_t)(g0 + q) * ldx + j0 + r] = v;
+    }
+    __syncthreads();
+    // update with the solved block
     if (!TR) {
-      const int64_t rbeg = j0 + jb + (int64_t)blockIdx.x * kStepRows;
-      constexpr int RPW = kStepRows / kTrsvWarps;  // rows per warp
-      constexpr int RB = 8;                        // rows in flight per warp
-      for (int rr0 = 0; rr0 < RPW; rr0 += RB) {
-        const int64_t rowBase = rbeg + warp * RPW + rr0;
-        if (rowBase >= n) break;
-        T mv[RB][3];
+      for (int q = 0; q < ng; q++) {
+        const T x0 = xs[q][lane], x1 = xs[q][lane + 32], x2 = xs[q][lane + 64];
+        T v[UF];
 #pragma unroll
-        for (int rr = 0; rr < RB; rr++)
+        for (int rr = 0; rr < UF; rr++) v[rr] = mv[rr * 3] * x0 + mv[rr * 3 + 1] * x1 + mv[rr * 3 + 2] * x2;
 #pragma unroll
-          for (int u = 0; u < 3; u++)
-            mv[rr][u] = (rowBase + rr < n && lane + 32 * u < jb) ? L[(rowBase + rr) * ldl + j0 + lane + 32 * u] : T(0);
-        for (int q = 0; q < ng; q++) {
-          const T x0 = xs[q * kTB + lane], x1 = xs[q * kTB + lane + 32], x2 = xs[q * kTB + lane + 64];
-          T v[RB];
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-          for (int rr = 0; rr < RB; rr++) v[rr] = mv[rr][0] * x0 + mv[rr][1] * x1 + mv[rr][2] * x2;
+          for (int rr = 0; rr < UF; rr++) v[rr] += __shfl_xor_sync(0xffffffffu, v[rr], o);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int rr = 0; rr < RB; rr++) v[rr] += __shfl_xor_sync(0xffffffffu, v[rr], o);
-#pragma unroll
-          for (int rr = 0; rr < RB; rr++)
-            if (lane == rr && rowBase + rr < n) C[(int64_t)(g0 + q) * ldc + rowBase + rr] -= v[rr];
-        }
+        for (int rr = 0; rr < UF; rr++)
+          if (lane == rr && rowBase + rr < n) C[(int64_t)(g0 + q) * ldc + rowBase + rr] -= v[rr];
       }
     } else {
-      const int64_t col = (int64_t)blockIdx.x * kStepCols + tid;
-      if (col < j0) {
-        T acc[kTrsvWarps];
+      T acc[kInvRHS];
 #pragma unroll
-        for (int q = 0; q < kTrsvWarps; q++) acc[q] = T(0);
-        const T* m = L + j0 * ldl + col;
-#pragma unroll 8
-        for (int r = 0; r < jb; r++) {
-          const T mv = m[(int64_t)r * ldl];
+      for (int q = 0; q < kInvRHS; q++) acc[q] = T(0);
 #pragma unroll
-          for (int q = 0; q < kTrsvWarps; q++) acc[q] += mv * xs[q * kTB + r];
-        }
+      for (int r = 0; r < UB; r++)
 #pragma unroll
-        for (int q = 0; q < kTrsvWarps; q++)
-          if (q < ng) C[(int64_t)(g0 + q) * ldc + col] -= acc[q];
+        for (int q = 0; q < kInvRHS; q++) acc[q] += mv[r] * xs[q][half * UB + r];
+      // reuse `part` for the two halves: part[half][q][column within the CTA]  (kStepCols == 128 > kTB: split rows)
+      T* red = &part[0][0][0];  // 8*4*96 = 3072 entries >= 2*4*128
+#pragma unroll
+      for (int q = 0; q < kInvRHS; q++) red[(half * kInvRHS + q) * kStepCols + (tid & (kStepCols - 1))] = acc[q];
+      __syncthreads();
+      if (half == 0 && col < j0) {
+#pragma unroll
+        for (int q = 0; q < kInvRHS; q++)
+          if (q < ng)
+            C[(int64_t)(g0 + q) * ldc + col] -= red[q * kStepCols + tid] + red[(kInvRHS + q) * kStepCols + tid];
       }
     }
     __syncthreads();
+  }
+}
+
+// W = L_bb^-1 for every 96 x 96 diagonal block b of a dense lower-triangular matrix (one CTA per block): thread c
+// computes column c of W by forward substitution (4 accumulators), W is written twice to the scratch, row-major
+// (slot 0) and transposed (slot 1), zero padded to 96 x 96 - the operands of the inverse-based block steps.
+template <typename T>
+__global__ void __launch_bounds__(128) invert_blocks_kernel(int64_t n, Operand<T> Lop, int64_t ldl, Operand<T> Wop) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* Ls = reinterpret_cast<T*>(smemRaw);  // [kTB][kTLD]
+  T* Ws = Ls + kTB * kTLD;                // [kTB][kTLD]
+  T* dinv = Ws + kTB * kTLD;              // [kTB]
+  const int64_t j0 = (int64_t)blockIdx.x * kTB;
+  const int jb = (int)min((int64_t)kTB, n - j0);
+  const T* __restrict__ D = Lop.at(blockIdx.z) + j0 * ldl + j0;
+  T* W = Wop.at(blockIdx.z) + (int64_t)blockIdx.x * (2 * kTB * kTB);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * kTB * kTLD + kTB; i += 128) Ls[i] = T(0);
+  __syncthreads();
+  {
+    T tmp[(kTB / 4) * 3];
+#pragma unroll
+    for (int a = 0; a < kTB / 4; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + 4 * a, c = lane + 32 * u;
+        tmp[a * 3 + u] = (c <= r && r < jb) ? D[(int64_t)r * ldl + c] : T(0);
+      }
+#pragma unroll
+    for (int a = 0; a < kTB / 4; a++)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int r = warp + 4 * a, c = lane + 32 * u;
+        if (c <= r && r < jb) Ls[r * kTLD + c] = tmp[a * 3 + u];
+      }
+  }
+  __syncthreads();
+  if (tid < jb) dinv[tid] = T(1) / Ls[tid * kTLD + tid];
+  __syncthreads();
+  if (tid < jb) {
+    const int c = tid;
+    Ws[c * kTLD + c] = dinv[c];
+    for (int i = c + 1; i < jb; i++) {
+      const T* li = Ls + i * kTLD;
+      T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int q = c;
+      for (; q + 4 <= i; q += 4) {
+        a0 += li[q] * Ws[q * kTLD + c];
+        a1 += li[q + 1] * Ws[(q + 1) * kTLD + c];
+        a2 += li[q + 2] * Ws[(q + 2) * kTLD + c];
+        a3 += li[q + 3] * Ws[(q + 3) * kTLD + c];
+      }
+      for (; q < i; q++) a0 += li[q] * Ws[q * kTLD + c];
+      Ws[i * kTLD + c] = -((a0 + a1) + (a2 + a3)) * dinv[i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kTB * kTB; i += 128) {
+    const int r = i / kTB, c = i % kTB;
+    W[i] = Ws[r * kTLD + c];                // row-major W
+    W[kTB * kTB + i] = Ws[c * kTLD + r];    // W^T
   }
 }
 
@@ -379,7 +595,7 @@ __global__ void copy_vec_kernel(int64_t n, int nRHS, Operand<T> Xop, int64_t ldx
 
 template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
-             bool transposed, Operand<T> scratch) {
+             bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady) {
   if (n <= 0 || nRHS <= 0) return;
   const int nb = kTB;
   if (n <= nb) {  // a single block: solved in place
@@ -394,13 +610,30 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   }();
   (void)once;
   const int64_t ldx = n;
+  // inverse-based diagonal steps when the caller provided room for the block inverses (2 x 96 x 96 per block)
+  const bool useInv = invScratch.base != nullptr;
+  if (useInv && !inversesReady) {
+    const size_t ismem = ((size_t)2 * kTB * kTLD + kTB) * sizeof(T);
+    static bool onceInv = [&] {
+      B200_CUDA(cudaFuncSetAttribute(invert_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      return true;
+    }();
+    (void)onceInv;
+    ProfScope prof(st, KC_SOLVE_DENSE, 0, (double)n * kTB / 2 * sizeof(T) * batch);
+    invert_blocks_kernel<T><<<dim3(ceilDiv(n, nb), 1, batch), 128, ismem, st>>>(n, L, ldl, invScratch);
+    B200_LAUNCH_CHECK();
+  }
   if (!transposed) {
     for (int64_t j0 = 0; j0 < n; j0 += nb) {
       int64_t jb = std::min<int64_t>(nb, n - j0), rb = n - j0 - jb;
       ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * rb * jb) * nRHS * batch,
                      (double)(jb * (jb + 1) / 2 + rb * jb) * sizeof(T) * batch);
-      solve_step_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kTrsvWarps * 32, smem, st>>>(
-          n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS);
+      if (useInv)
+        solve_step_inv_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kInvThreads, 0, st>>>(
+            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch);
+      else
+        solve_step_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kTrsvWarps * 32, smem, st>>>(
+            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch, false);
       B200_LAUNCH_CHECK();
     }
   } else {
@@ -408,8 +641,12 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
       int64_t jb = std::min<int64_t>(nb, n - j0);
       ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * j0 * jb) * nRHS * batch,
                      (double)(jb * (jb + 1) / 2 + j0 * jb) * sizeof(T) * batch);
-      solve_step_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kTrsvWarps * 32, smem, st>>>(
-          n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS);
+      if (useInv)
+        solve_step_inv_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kInvThreads, 0, st>>>(
+            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch);
+      else
+        solve_step_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kTrsvWarps * 32, smem, st>>>(
+            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch, false);
       B200_LAUNCH_CHECK();
     }
   }
@@ -423,7 +660,8 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   template void gemvColsT<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t, int64_t, \
                              Operand<T>, int64_t, int);                                                                 \
   template void symmLower<T>(cudaStream_t, int, int64_t, T, Operand<T>, Operand<T>, int64_t, Operand<T>, int64_t, int); \
-  template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>);
+  template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>, \
+                           Operand<T>, bool);
 B200_INSTANTIATE_SOLVE(double)
 B200_INSTANTIATE_SOLVE(float)
 
