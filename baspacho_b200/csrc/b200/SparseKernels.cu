@@ -50,22 +50,61 @@ __global__ void __launch_bounds__(128) elim_factor_lumps_kernel(DevSkel sk, Mats
   const int64_t cb = sk.chainColPtr[lump], ce = sk.chainColPtr[lump + 1];
   T* D = data + sk.chainData[cb];
   const int64_t rowsBelow = sk.chainRowsTillEnd[ce - 1] - s;
-  if (lane == 0) choleskySerial(D, s, (int64_t)s);
-  __syncwarp();
   T* below = D + (int64_t)s * s;
   if constexpr (S > 0) {
-    T L[S * (S + 1) / 2];
+    // the first row of every lane is requested BEFORE lane 0 factors the diagonal block: the (long) global latency of
+    // the panel rows overlaps the serial sqrt/divide chain instead of following it
+    T x0[S];
+    const bool has0 = lane < rowsBelow;
+    if (has0) {
+#pragma unroll
+      for (int j = 0; j < S; j++) x0[j] = below[(int64_t)lane * S + j];
+    }
+    // every lane factors the (tiny) diagonal block redundantly in registers: one broadcast load, no second trip to
+    // memory, no intra-warp hand-off; lane 0 writes the factor back
+    T Dr[S * S];
 #pragma unroll
     for (int j = 0; j < S; j++)
 #pragma unroll
-      for (int q = 0; q <= j; q++) L[j * (j + 1) / 2 + q] = D[j * S + q];
+      for (int q = 0; q <= j; q++) Dr[j * S + q] = D[j * S + q];
+    T L[S * (S + 1) / 2];
 #pragma unroll
-    for (int j = 0; j < S; j++) L[j * (j + 1) / 2 + j] = T(1) / L[j * (j + 1) / 2 + j];
+    for (int j = 0; j < S; j++) {
+      T d = Dr[j * S + j];
+#pragma unroll
+      for (int q = 0; q < j; q++) d -= Dr[j * S + q] * Dr[j * S + q];
+      d = sqrt(d);
+      Dr[j * S + j] = d;
+      const T inv = T(1) / d;
+      L[j * (j + 1) / 2 + j] = inv;  // reciprocal of the diagonal entry
+#pragma unroll
+      for (int i = j + 1; i < S; i++) {
+        T v = Dr[i * S + j];
+#pragma unroll
+        for (int q = 0; q < j; q++) v -= Dr[i * S + q] * Dr[j * S + q];
+        Dr[i * S + j] = v * inv;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S; j++)
+#pragma unroll
+      for (int q = 0; q < j; q++) L[j * (j + 1) / 2 + q] = Dr[j * S + q];
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < S; j++)
+#pragma unroll
+        for (int q = 0; q <= j; q++) D[j * S + q] = Dr[j * S + q];
+    }
     for (int64_t r = lane; r < rowsBelow; r += 32) {
       T* xr = below + r * S;
       T x[S];
+      if (r == lane) {
 #pragma unroll
-      for (int j = 0; j < S; j++) x[j] = xr[j];
+        for (int j = 0; j < S; j++) x[j] = x0[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < S; j++) x[j] = xr[j];
+      }
 #pragma unroll
       for (int j = 0; j < S; j++) {
         T v = x[j];
@@ -77,6 +116,8 @@ __global__ void __launch_bounds__(128) elim_factor_lumps_kernel(DevSkel sk, Mats
       for (int j = 0; j < S; j++) xr[j] = x[j];
     }
   } else {
+    if (lane == 0) choleskySerial(D, s, (int64_t)s);
+    __syncwarp();
     for (int64_t r = lane; r < rowsBelow; r += 32) solveRowSerial(D, s, (int64_t)s, below + r * s);
   }
 }
@@ -323,6 +364,29 @@ __global__ void __launch_bounds__(128) elim_gather_solveLt_kernel(DevSkel sk, Ma
   const int64_t c0 = sk.lumpStart[lump];
   const int64_t first = sk.chainColPtr[lump] + (sk.lumpToSpan[lump + 1] - sk.lumpToSpan[lump]);
   const int64_t end = sk.chainColPtr[lump + 1];
+  constexpr int MAXW = 12;
+  if (s <= MAXW) {
+    // single pass over the chains, all s outputs accumulated in registers
+    T acc[MAXW];
+#pragma unroll
+    for (int q = 0; q < MAXW; q++) acc[q] = q < s ? C[c0 + q] : T(0);
+    for (int64_t ch = first; ch < end; ch++) {
+      const int64_t span = sk.chainRowSpan[ch];
+      const int64_t r0 = sk.spanStart[span];
+      const int rows = (int)(sk.spanStart[span + 1] - r0);
+      const T* __restrict__ blk = data + sk.chainData[ch];
+      for (int r = 0; r < rows; r++) {
+        const T v = C[r0 + r];
+#pragma unroll
+        for (int q = 0; q < MAXW; q++)
+          if (q < s) acc[q] -= blk[r * s + q] * v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXW; q++)
+      if (q < s) C[c0 + q] = acc[q];
+    return;
+  }
   for (int q = 0; q < s; q++) {
     T acc = C[c0 + q];
     for (int64_t ch = first; ch < end; ch++) {
