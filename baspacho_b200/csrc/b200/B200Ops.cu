@@ -9,7 +9,9 @@
 //     (reference: numSpans*8 bytes H2D per lump in prepareAssemble :471-481, pointer arrays before every op);
 //   * errors are std::runtime_error, never abort() (reference: CudaDefs.h:27-65).
 #include <cstring>
+#include <map>
 #include <memory>
+#include <set>
 #include "../host/DebugMacros.h"
 #include "../host/MatOps.h"
 #include "B200Kernels.h"
@@ -315,10 +317,15 @@ struct B200NumericCtx : NumericCtx<TT> {
         const WaveLevel& L = wv.host.levels[lv];
         waveUpdate<T>(sym.stream, m.batch, all, wv.tiles.ptr() + L.tileBegin, L.tileEnd - L.tileBegin,
                       wv.targets.ptr(), wv.sources.ptr(), wv.rowMap.ptr());
-        for (int64_t l : L.bigLumps) updateLump(m, l, firstSrc, upToLump);
+        static const int order = getenv("BSPB200_WAVE_ORDER") ? atoi(getenv("BSPB200_WAVE_ORDER")) : 0;
+        if (order == 0)
+          for (int64_t l : L.bigLumps) updateLump(m, l, firstSrc, upToLump);
         potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
                                wv.panelFlops[lv]);
-        for (int64_t l : L.bigLumps) factorLumpColumn(m, l);
+        for (int64_t l : L.bigLumps) {
+          if (order != 0) updateLump(m, l, firstSrc, upToLump);
+          factorLumpColumn(m, l);
+        }
       }
       return;
     }
@@ -376,14 +383,22 @@ struct B200SolveCtx : SolveCtx<TT> {
   // solved-block staging of the blocked dense triangular solve (order x nRHS), [2] the inverses of the 96 x 96
   // diagonal blocks of the widest lump (2 x 96 x 96 per block)
   int64_t vecStride() const { return std::max<int64_t>(1, skel.order() * nRHS); }
-  int64_t invStride() const {
-    int64_t widest = 0;
-    for (int64_t l = 0; l < skel.numLumps(); l++) widest = std::max(widest, skel.lumpSize(l));
-    return widest > 96 ? 2 * 96 * 96 * ((widest + 95) / 96) : 0;
+  // block inverses of EVERY wide lump live side by side in the scratch (slot table by diagonal-block offset), so the
+  // backward pass of solve() reuses what the forward pass computed
+  static constexpr int64_t kInvMinBlocks = 6;  // narrower lumps keep the substitution-based steps
+  void buildInvTable() {
+    if (invTotal >= 0) return;
+    invTotal = 0;
+    for (int64_t l = 0; l < skel.numLumps(); l++) {
+      int64_t w = skel.lumpSize(l), nblk = (w + 95) / 96;
+      if (nblk < kInvMinBlocks) continue;
+      invSlot[skel.lumpDataOffset(l)] = {invTotal, w};
+      invTotal += 2 * 96 * 96 * nblk;
+    }
   }
   T* scratchBase() {
-    if (invStrideCache < 0) invStrideCache = invStride();
-    return (T*)sym.scratch((size_t)(2 * vecStride() + invStrideCache) * batch * sizeof(T));
+    buildInvTable();
+    return (T*)sym.scratch((size_t)(2 * vecStride() + invTotal) * batch * sizeof(T));
   }
   Work<T> temp(int which = 0) {
     Work<T> w;
@@ -391,23 +406,26 @@ struct B200SolveCtx : SolveCtx<TT> {
     w.base = scratchBase() + (size_t)which * w.stride * batch;
     return w;
   }
-  Operand<T> invScratch() {
+  // scratch operand for the inverses of the lump whose diagonal block starts at offM (null operand: not eligible)
+  Operand<T> invScratch(int64_t offM, int64_t n, bool* ready) {
     Operand<T> o;
-    if (invStrideCache < 0) invStrideCache = invStride();
-    if (invStrideCache == 0 || !sym.useInverseSolve) return o;
-    o.base = scratchBase() + (size_t)2 * vecStride() * batch;
-    o.bstride = invStrideCache;
+    *ready = false;
+    buildInvTable();
+    auto it = invSlot.find(offM);
+    if (!sym.useInverseSolve || it == invSlot.end() || it->second.second != n) return o;
+    o.base = scratchBase() + (size_t)2 * vecStride() * batch + it->second.first;
+    o.bstride = invTotal;
+    *ready = invDone.count(offM) > 0;
+    invDone.insert(offM);
     return o;
   }
-  int64_t invStrideCache = -1;
-  // the block inverses in the scratch belong to (matrix, offset, n) of the last wide lump solved through this context
-  // (solve() runs solveL then solveLt on the same factor: the second pass reuses them)
+  int64_t invTotal = -1;
+  std::map<int64_t, std::pair<int64_t, int64_t>> invSlot;  // diagonal block offset -> (scratch offset, width)
+  std::set<int64_t> invDone;                               // inverses computed through this context
   const void* invData = nullptr;
-  int64_t invOff = -1, invN = -1;
-  bool invReady(const TT* data, int64_t offM, int64_t n) {
-    bool same = invData == (const void*)data && invOff == offM && invN == n;
-    invData = data, invOff = offM, invN = n;
-    return same && n > 96;
+  void invCheckData(const TT* data) {  // a context serves one factor; a different matrix invalidates the inverses
+    if (invData != (const void*)data) invDone.clear();
+    invData = data;
   }
   Work<T> temp2() { return temp(1); }
 
@@ -443,13 +461,19 @@ struct B200SolveCtx : SolveCtx<TT> {
   void solveL(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), invScratch(), invReady(data, offM, n));
+    invCheckData(data);
+    bool ready = false;
+    Operand<T> inv = invScratch(offM, n, &ready);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), inv, ready);
   }
 
   void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
     auto timer = sym.solveLtStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), invScratch(), invReady(data, offM, n));
+    invCheckData(data);
+    bool ready = false;
+    Operand<T> inv = invScratch(offM, n, &ready);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), inv, ready);
   }
 
   void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,

@@ -685,8 +685,12 @@ static Lookahead& lookahead() {
 }
 static int& lookaheadMode() {
   static int mode = [] {
+    // 0 (default): recursive blocked schedule on the caller's stream. 1: right-looking depth-1 lookahead on an
+    // internal high-priority stream - EXPERIMENTAL: correct standalone (tools/check_trapezoid.py) but a cross-stream
+    // ordering problem shows up inside multi-lump factorizations (tools/check_grid.py), and it only buys ~1% on the
+    // BAL-shaped benchmark; 2: the lookahead schedule serialised on one stream (debug)
     const char* e = getenv("BSPB200_LOOKAHEAD");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   return mode;
 }
@@ -743,7 +747,8 @@ void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Op
   // tensor pipes busy. Dependencies: part2(k) waits for panel(k) (event); part1(k+1) waits for part2(k) (event).
   Lookahead& la = lookahead();
   const int64_t total = n + rowsBelow, nb = kNB;
-  cudaStream_t crit = la.side;  // high priority: panels + part 1 (the critical path); part 2 stays on the caller's stream
+  // high priority: panels + part 1 (the critical path); part 2 stays on the caller's stream
+  cudaStream_t crit = lookaheadMode() == 2 ? st : la.side;  // mode 2 (debug): same schedule serialised on one stream
   B200_CUDA(cudaEventRecord(la.evStart, st));
   B200_CUDA(cudaStreamWaitEvent(crit, la.evStart, 0));
   bool pendingP2 = false;
