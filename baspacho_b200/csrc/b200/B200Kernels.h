@@ -62,7 +62,8 @@ void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Op
 // diagonal Cholesky + triangular solve of many small lump columns in one launch (work list on the device)
 struct WavePanel;
 template <typename T>
-void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const WavePanel* work, int64_t count, double flops);
+void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const WavePanel* work, int64_t count,
+                         int numLumps, double flops);
 
 // wavefront update of the small target lumps of one level (WaveKernels.cu)
 struct WaveTile;

@@ -321,7 +321,7 @@ struct B200NumericCtx : NumericCtx<TT> {
         if (order == 0)
           for (int64_t l : L.bigLumps) updateLump(m, l, firstSrc, upToLump);
         potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
-                               wv.panelFlops[lv]);
+                               L.numSmall, wv.panelFlops[lv]);
         for (int64_t l : L.bigLumps) {
           if (order != 0) updateLump(m, l, firstSrc, upToLump);
           factorLumpColumn(m, l);

@@ -79,7 +79,8 @@ WavePlan buildWavePlan(const CoalescedBlockMatrixSkel& sk, int64_t firstLump) {
       const int64_t below = totalRows - w;
       const int64_t slabs = std::max<int64_t>(1, (below + WavePlan::kPanelRows - 1) / WavePlan::kPanelRows);
       for (int64_t sl = 0; sl < slabs; sl++)
-        p.panels.push_back(WavePanel{tg.dataOff, (int32_t)w, (int32_t)below, (int32_t)sl, 0});
+        p.panels.push_back(WavePanel{tg.dataOff, (int32_t)w, (int32_t)below, (int32_t)sl, L.numSmall});
+      L.numSmall++;
     }
     L.tileEnd = (int32_t)p.tiles.size();
     L.panelEnd = (int32_t)p.panels.size();

@@ -33,10 +33,12 @@ struct WaveTile {
 };
 struct WavePanel {
   int64_t dataOff;
-  int32_t n, rows, slab, pad;
+  int32_t n, rows, slab;
+  int32_t lumpIdx;  // index of the lump inside its level (selects the load counter of the panel kernel)
 };
 struct WaveLevel {
   int32_t tileBegin = 0, tileEnd = 0, panelBegin = 0, panelEnd = 0;
+  int32_t numSmall = 0;  // small lumps of the level
   std::vector<int64_t> bigLumps;
 };
 

@@ -280,7 +280,8 @@ __device__ __forceinline__ Vec2<float> load2(const float* p) {
 
 template <typename T, bool DO_POTRF>
 __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
-                                                             Operand<T> Bop, int64_t ldb, const WavePanel* work) {
+                                                             Operand<T> Bop, int64_t ldb, const WavePanel* work,
+                                                             int* counters, int lumpsInLaunch) {
   constexpr int NW = kPanelThreads / 32;  // 8 warps
   constexpr int G = kPanelG, R = kPanelRows, W = 32 / G;
   constexpr int LA = kNB / NW, LU = kNB / 32;
@@ -290,10 +291,10 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
   T* Xs = invd + kNB;                     // [R][kLDX]  (also the 2 x kNB column buffer of the Cholesky phase)
   T* __restrict__ L = Lop.at(blockIdx.z);
   T* __restrict__ B = Bop.at(blockIdx.z);
-  int slab = blockIdx.x;
+  int slab = blockIdx.x, lumpIdx = 0;
   if (work) {  // batched over a work list (wavefront): one item = (lump column, 64-row slab)
     const WavePanel w = work[blockIdx.x];
-    n = w.n, rows = w.rows, slab = w.slab;
+    n = w.n, rows = w.rows, slab = w.slab, lumpIdx = w.lumpIdx;
     L += w.dataOff;
     B = L + (int64_t)n * n;
     ldl = ldb = n;
@@ -323,6 +324,21 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
         }
     }
     __syncthreads();
+    // Every CTA of a lump column factors the diagonal block from the ORIGINAL values, so the factor may only be written
+    // back once every CTA of that column has loaded the block: the CTAs count themselves in after the load, and the
+    // one that arrives last (all others provably hold their copy) is the writer. No CTA ever waits on another, so the
+    // protocol is independent of how many CTAs are co-resident; the writer resets the counter for the next launch.
+    __shared__ int writerFlag;
+    if (tid == 0) {
+      const int slabs = max(1, (int)((rows + R - 1) / R));
+      int* ctr = counters + (int64_t)blockIdx.z * lumpsInLaunch + lumpIdx;
+      __threadfence();
+      const int old = atomicAdd(ctr, 1);
+      writerFlag = (old == slabs - 1);
+      if (writerFlag) *ctr = 0;
+    }
+    __syncthreads();
+    const bool writer = writerFlag != 0;
     T* colbuf = Xs;                // [4][kNB]  raw (not yet scaled) columns of the current 4-column group
     T* ybuf = Xs + 4 * kNB;        // [kNB][4]  finished rows of the group: L[i][j0 .. j0+3]
     T reg[RA][CU];
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
         const int i = lane + 32 * a, c = warp + NW * u;
         if (c <= i && i < n) {
           Lt[c * kLDT + ltPos(i)] = reg[a][u];
-          if (slab == 0) L[(int64_t)i * ldl + c] = reg[a][u];
+          if (writer) L[(int64_t)i * ldl + c] = reg[a][u];
         }
       }
   } else {
@@ -587,8 +603,13 @@ void gemmNT<double>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k,
                    (A.bstride % 2 == 0) && (B.bstride % 2 == 0) && ((uintptr_t)A.base % 16 == 0) &&
                    ((uintptr_t)B.base % 16 == 0);
   // big tiles when they fill the machine, small ones for skinny / small products
-  if (m >= 96 && n >= 96 && (int64_t)ceilDiv(m, 128) * ceilDiv(n, 128) * batch >= 96)
-    launchGemmF64<128, 128, 16, 64, 32, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
+  static const int cfg = getenv("BSPB200_GEMM_CFG") ? atoi(getenv("BSPB200_GEMM_CFG")) : 1;
+  if (m >= 96 && n >= 96 && (int64_t)ceilDiv(m, 128) * ceilDiv(n, 128) * batch >= 96) {
+    if (cfg == 1)  // 128 x 64 tiles, 4 warps, 3 stages: two CTAs per SM (finer tail, epilogue/main-loop overlap)
+      launchGemmF64<128, 64, 16, 64, 32, 3>(st, batch, s, alpha, A, B, beta, C, aligned16);
+    else
+      launchGemmF64<128, 128, 16, 64, 32, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
+  }
   else
     launchGemmF64<64, 64, 16, 32, 16, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
 }
@@ -614,6 +635,20 @@ int maxBlockDim<float>() {
   return kNB;
 }
 
+// zero-initialised load counters of the panel kernel (grow-only; the kernel leaves them zero again)
+static int* panelCounters(int64_t needed) {
+  static int* buf = nullptr;
+  static int64_t cap = 0;
+  if (needed > cap) {
+    B200_CUDA(cudaDeviceSynchronize());
+    if (buf) cudaFree(buf);
+    cap = std::max<int64_t>(needed, 1 << 16);
+    B200_CUDA(cudaMalloc((void**)&buf, cap * sizeof(int)));
+    B200_CUDA(cudaMemset(buf, 0, cap * sizeof(int)));
+  }
+  return buf;
+}
+
 template <typename T, bool DO_POTRF>
 static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                         int64_t ldb) {
@@ -622,25 +657,27 @@ static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand
   static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
   (void)once;
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
-  panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr);
+  panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr,
+                                                                               panelCounters(batch), 1);
   B200_LAUNCH_CHECK();
 }
 
 // batched over a device work list (one CTA per (lump, slab) item): the small supernodes of one tree level
 template <typename T>
 void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const WavePanel* work, int64_t count,
-                         double flops) {
+                         int numLumps, double flops) {
   if (count <= 0) return;
   static_assert(WavePlan::kPanelRows == kPanelRows, "slab size of the plan and of the kernel differ");
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
   static bool once = (setSmem(panel_kernel<T, true>, smem), true);
   (void)once;
   ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
-  panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(0, 0, data, 0, data, 0, work);
+  panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(
+      0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps);
   B200_LAUNCH_CHECK();
 }
-template void potrfTrsmPanelBatch<double>(cudaStream_t, int, Operand<double>, const WavePanel*, int64_t, double);
-template void potrfTrsmPanelBatch<float>(cudaStream_t, int, Operand<float>, const WavePanel*, int64_t, double);
+template void potrfTrsmPanelBatch<double>(cudaStream_t, int, Operand<double>, const WavePanel*, int64_t, int, double);
+template void potrfTrsmPanelBatch<float>(cudaStream_t, int, Operand<float>, const WavePanel*, int64_t, int, double);
 
 template <typename T>
 void potrfBlock(cudaStream_t st, int batch, int n, Operand<T> A, int64_t lda) {
@@ -686,9 +723,8 @@ static Lookahead& lookahead() {
 static int& lookaheadMode() {
   static int mode = [] {
     // 0 (default): recursive blocked schedule on the caller's stream. 1: right-looking depth-1 lookahead on an
-    // internal high-priority stream - EXPERIMENTAL: correct standalone (tools/check_trapezoid.py) but a cross-stream
-    // ordering problem shows up inside multi-lump factorizations (tools/check_grid.py), and it only buys ~1% on the
-    // BAL-shaped benchmark; 2: the lookahead schedule serialised on one stream (debug)
+    // internal high-priority stream (measured ~1% on the BAL-shaped benchmark: the panel chain, not the overlap,
+    // bounds the critical path); 2: the lookahead schedule serialised on one stream (debug)
     const char* e = getenv("BSPB200_LOOKAHEAD");
     return e ? atoi(e) : 0;
   }();

@@ -267,3 +267,29 @@ def test_factor_solve_host_end_to_end():
     o.factor(ref)
     mask = np.tril(g.densify(np.ones_like(data))) > 0
     assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("model", [_capi.MODEL_B200, _capi.MODEL_OPENBLAS_I7])
+def test_grid_wide_and_small_lumps(model):
+    """GRID family (Bench.cpp:322-343 genGrid): wide supernodes with rows below (blocked trapezoid Cholesky, GEMM+assemble
+    updates) mixed with small ones (wavefront kernels), factor AND solve against the oracle - the multi-lump case that the
+    single dense-supernode tests do not cover."""
+    sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_GRID, [36, 36, 1.0, 2], 6, 6, 37)
+    g, o = make_pair(sizes, ptrs, inds, find_sparse_elim_ranges=False, computation_model=model)
+    widths = np.diff(g.lumpStart)
+    assert widths.max() > 96
+    data = H.make_data(g, 37, np.float64, 1.2)
+    ref = data.copy()
+    o.factor(ref)
+    for rep in range(2):  # twice: catches stream-ordering races that a single run can miss
+        d = torch_of(data)
+        g.factor(d)
+        got = d.cpu().numpy()
+        mask = np.tril(g.densify(np.ones_like(data))) > 0
+        assert np.abs(g.densify(got) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+    rhs = H.oapi().random_data_array(g.order * 2, -1, 1, 38).reshape(2, g.order)
+    x = torch_of(rhs)
+    g.solve(d, x)
+    xr = rhs.copy()
+    o.solve(ref, xr)
+    assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())

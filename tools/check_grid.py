@@ -7,8 +7,8 @@ from tests import helpers as H
 api = bsp.api()
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 sizes, ptrs, inds = api.gen_pattern_arrays(1, [G, G, 1.0, 2], 6, 6, 37)
-s = bsp.Solver.create(sizes, ptrs, inds, computation_model=2, find_sparse_elim_ranges=False)
-o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, backend=_capi.BACKEND_FAST, num_threads=16, computation_model=2, find_sparse_elim_ranges=False)
+s = bsp.Solver.create(sizes, ptrs, inds, computation_model=int(os.environ.get("MODEL", 2)), find_sparse_elim_ranges=False)
+o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, backend=_capi.BACKEND_FAST, num_threads=16, computation_model=int(os.environ.get("MODEL", 2)), find_sparse_elim_ranges=False)
 print("lumps", s.num_lumps, "widths", np.diff(s.lumpStart)[-12:])
 data = H.make_data(s, 37, np.float64, 1.2)
 ref = data.copy(); o.factor(ref)
