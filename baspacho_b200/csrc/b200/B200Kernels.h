@@ -42,6 +42,9 @@ template <typename T>
 void gemmNT(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k, T alpha, Operand<T> A, int64_t lda,
             Operand<T> B, int64_t ldb, T beta, Operand<T> C, int64_t ldc, bool lowerOnly);
 
+// diagnostics: what == 0 -> phase time stamps (clock64) of the last instrumented panel_kernel launch
+int64_t debugRead(int what, void* out, int64_t bytes);
+
 // max diagonal block handled by one CTA (potrfBlock / trsmBlock / trsvBlock)
 template <typename T>
 int maxBlockDim();

@@ -281,7 +281,11 @@ __device__ __forceinline__ Vec2<float> load2(const float* p) {
 template <typename T, bool DO_POTRF>
 __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl,
                                                              Operand<T> Bop, int64_t ldb, const WavePanel* work,
-                                                             int* counters, int lumpsInLaunch) {
+                                                             int* counters, int lumpsInLaunch, long long* clk) {
+  // optional phase time stamps of CTA 0 (diagnostics: BSPB200_PANEL_CLK=1, read with bspb200_debug_read(0, ...))
+#define B200_PCLK(i) \
+  if (clk && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.z == 0) clk[i] = clock64();
+  B200_PCLK(0)
   constexpr int NW = kPanelThreads / 32;  // 8 warps
   constexpr int G = kPanelG, R = kPanelRows, W = 32 / G;
   constexpr int LA = kNB / NW, LU = kNB / 32;
@@ -306,6 +310,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
     T* S = Lt;
     for (int i = tid; i < kNB * kLDS; i += kPanelThreads) S[i] = T(0);
     __syncthreads();
+    B200_PCLK(1)
     {  // lower triangle -> smem (coalesced), all loads in flight at once
       T tmp[LA * LU];
 #pragma unroll
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
         }
     }
     __syncthreads();
+    B200_PCLK(2)
     // Every CTA of a lump column factors the diagonal block from the ORIGINAL values, so the factor may only be written
     // back once every CTA of that column has loaded the block: the CTAs count themselves in after the load, and the
     // one that arrives last (all others provably hold their copy) is the writer. No CTA ever waits on another, so the
@@ -339,6 +345,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
     }
     __syncthreads();
     const bool writer = writerFlag != 0;
+    B200_PCLK(3)
     T* colbuf = Xs;                // [4][kNB]  raw (not yet scaled) columns of the current 4-column group
     T* ybuf = Xs + 4 * kNB;        // [kNB][4]  finished rows of the group: L[i][j0 .. j0+3]
     T reg[RA][CU];
@@ -439,8 +446,10 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
       }
     }
     __syncthreads();  // column buffers and the row-major staging are dead
+    B200_PCLK(4)
     for (int i = tid; i < kNB * kLDT + kNB; i += kPanelThreads) Lt[i] = T(0);
     __syncthreads();
+    B200_PCLK(5)
 #pragma unroll
     for (int a = 0; a < RA; a++)
 #pragma unroll
@@ -463,6 +472,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
         if (r >= c && r < n) Lt[c * kLDT + ltPos(r)] = L[(int64_t)r * ldl + c];
       }
   }
+  B200_PCLK(6)
   if (rows <= 0) return;
   __syncthreads();
   if (tid < n) invd[tid] = T(1) / Lt[tid * kLDT + ltPos(tid)];
@@ -485,6 +495,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
       for (int u = 0; u < LU; u++) Xs[(warp + NW * a) * kLDX + lane + 32 * u] = tmp[a * LU + u];
   }
   __syncthreads();
+  B200_PCLK(7)
   {
     const int row = tid / G, g = tid % G;  // G adjacent lanes share a row
     T* x = Xs + row * kLDX;
@@ -544,12 +555,15 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
     }
   }
   __syncthreads();
+  B200_PCLK(8)
   for (int r = warp; r < nr; r += NW)
 #pragma unroll
     for (int u = 0; u < LU; u++) {
       const int c = lane + 32 * u;
       if (c < n) B[(r0 + r) * ldb + c] = Xs[r * kLDX + c];
     }
+  B200_PCLK(9)
+#undef B200_PCLK
 }
 
 // algorithmic flops of C = A B^T (lower-only: entries with col <= row)
@@ -649,6 +663,28 @@ static int* panelCounters(int64_t needed) {
   return buf;
 }
 
+// phase time stamps of the panel kernel (diagnostics, off unless BSPB200_PANEL_CLK is set)
+static long long* panelClockBuf() {
+  static long long* buf = [] {
+    long long* q = nullptr;
+    if (getenv("BSPB200_PANEL_CLK") && atoi(getenv("BSPB200_PANEL_CLK")) != 0) {
+      B200_CUDA(cudaMalloc((void**)&q, 64 * sizeof(long long)));
+      B200_CUDA(cudaMemset(q, 0, 64 * sizeof(long long)));
+    }
+    return q;
+  }();
+  return buf;
+}
+int64_t debugRead(int what, void* out, int64_t bytes) {
+  if (what == 0 && panelClockBuf()) {
+    const int64_t n = std::min<int64_t>(bytes, 64 * sizeof(long long));
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(out, panelClockBuf(), n, cudaMemcpyDeviceToHost));
+    return n;
+  }
+  return 0;
+}
+
 template <typename T, bool DO_POTRF>
 static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                         int64_t ldb) {
@@ -658,7 +694,7 @@ static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand
   (void)once;
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
   panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr,
-                                                                               panelCounters(batch), 1);
+                                                                               panelCounters(batch), 1, panelClockBuf());
   B200_LAUNCH_CHECK();
 }
 
@@ -673,7 +709,7 @@ void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const Wave
   (void)once;
   ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
   panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(
-      0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps);
+      0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
   B200_LAUNCH_CHECK();
 }
 template void potrfTrsmPanelBatch<double>(cudaStream_t, int, Operand<double>, const WavePanel*, int64_t, int, double);

@@ -217,6 +217,136 @@ __global__ void __launch_bounds__(LANES > 32 ? LANES : 128)
   }
 }
 
+// Staged variant of the fixed-shape gather. Same task ownership and summation order as elim_gather_fixed_kernel (lane
+// `sub` of a destination takes tasks sub, sub + LANES, ...; butterfly over the lanes; one read-modify-write of the
+// target), but the operand blocks reach the lanes through shared memory: a lane reading its own two blocks with
+// 8-byte loads touches 32 different cache lines per warp instruction and the L1 wavefront queue, not HBM, becomes the
+// bound (ncu r01: 48 % L2 hits, IPC 0.1). Here the 32 tasks of a warp iteration are fetched COOPERATIVELY -
+// consecutive lanes copy consecutive words of the same block with cp.async (2-3 lines per instruction) into a
+// per-warp stage [task][word] with an odd stride (conflict-free both for the cooperative writes and for the
+// per-lane reads), double buffered: the copies of iteration i + 1 are in flight while iteration i is multiplied.
+template <int BYTES>
+__device__ __forceinline__ void cpAsyncWord(void* smemDst, const void* src) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smemDst);
+  if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
+}
+
+constexpr int kStagedWarps = 4;
+template <typename T, int NR, int NC, int K>
+constexpr int stagedStride() {
+  return ((NR + NC) * K) | 1;  // odd word stride of one task in the stage
+}
+template <typename T, int NR, int NC, int K>
+constexpr size_t stagedSmemBytes() {
+  return (size_t)kStagedWarps * 2 * 32 * stagedStride<T, NR, NC, K>() * sizeof(T);
+}
+
+template <typename T, int NR, int NC, int K, int LANES>
+__global__ void __launch_bounds__(kStagedWarps * 32, 3)
+    elim_gather_staged_kernel(DevElimPlan p, Mats<T> mats, const int32_t* __restrict__ list, int64_t count) {
+  static_assert(LANES == 128 || (LANES <= 32 && 32 % LANES == 0), "LANES: a divisor of the warp, or the whole CTA");
+  constexpr int WA = NC * K, WB = NR * K, WT = WA + WB;  // words of the A block, the B block, one task
+  constexpr int STRIDE = ((NR + NC) * K) | 1;  // == stagedStride<T, NR, NC, K>()
+  constexpr uint32_t kNone = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* stage = reinterpret_cast<T*>(smemRaw) + (size_t)warp * 2 * 32 * STRIDE;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slot = gid / LANES;
+  const int sub = (int)(gid % LANES);
+  const bool live = slot < count;
+  const int64_t d = live ? list[slot] : 0;
+  T* data = mats.at(blockIdx.z);
+  T acc[NR * NC];
+#pragma unroll
+  for (int e = 0; e < NR * NC; e++) acc[e] = T(0);
+
+  const int tEnd = live ? p.dstTaskPtr[d + 1] : 0;
+  int t = live ? p.dstTaskPtr[d] + sub : 0;
+  // offsets of the task whose copies are issued next (kNone: this lane has no more tasks)
+  uint32_t oa = kNone, ob = kNone;
+  if (t < tEnd) oa = p.taskA[t], ob = p.taskB[t];
+
+  auto issue = [&](int buf) {  // cooperative copies of the 32 tasks (oa, ob) held by the lanes -> stage[buf]
+    T* dstBase = stage + (size_t)buf * 32 * STRIDE;
+    int task = lane / WT, word = lane % WT;  // flat word index f = r * 32 + lane = task * WT + word
+#pragma unroll 2
+    for (int r = 0; r < WT; r++) {  // WT rounds of 32 words
+      const uint32_t sa = __shfl_sync(0xffffffffu, oa, task), sb = __shfl_sync(0xffffffffu, ob, task);
+      if (sa != kNone) {
+        const T* src = word < WA ? data + sa + word : data + sb + (word - WA);
+        cpAsyncWord<sizeof(T)>(dstBase + task * STRIDE + word, src);
+      }
+      word += 32;
+      task += word / WT;
+      word %= WT;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  bool cur = oa != kNone;  // this lane's task of the iteration being multiplied is valid
+  issue(0);
+  int buf = 0;
+  while (__any_sync(0xffffffffu, cur)) {
+    // next iteration: fetch its offsets, put its copies in flight
+    t += LANES;
+    oa = ob = kNone;
+    if (t < tEnd) oa = p.taskA[t], ob = p.taskB[t];
+    const bool nxt = oa != kNone;
+    issue(buf ^ 1);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncwarp();
+    if (cur) {
+      const T* __restrict__ a = stage + (size_t)buf * 32 * STRIDE + lane * STRIDE;
+      const T* __restrict__ b = a + WA;
+      T av[WA], bv[WB];
+#pragma unroll
+      for (int i = 0; i < WA; i++) av[i] = a[i];
+#pragma unroll
+      for (int i = 0; i < WB; i++) bv[i] = b[i];
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int q = 0; q < K; q++) acc[r * NC + c] += bv[r * K + q] * av[c * K + q];
+    }
+    __syncwarp();  // the stage is rewritten two issues from now
+    cur = nxt;
+    buf ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+
+  constexpr int WL = LANES > 32 ? 32 : LANES;
+#pragma unroll
+  for (int o = 1; o < WL; o <<= 1)
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  if constexpr (LANES > 32) {
+    __shared__ T red[LANES / 32][NR * NC];
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++)
+      if (lane == e % 32) red[warp][e] = acc[e];
+    __syncthreads();
+    if (live && threadIdx.x < NR * NC) {
+      const int e = threadIdx.x;
+      T tot = 0;
+#pragma unroll
+      for (int w = 0; w < LANES / 32; w++) tot += red[w][e];
+      data[p.dstOff[d] + (e / NC) * (int64_t)p.dstStride[d] + (e % NC)] -= tot;
+    }
+  } else if (live) {
+    T* dst = data + p.dstOff[d];
+    const int64_t stride = p.dstStride[d];
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++)
+      if (e % LANES == sub) dst[(e / NC) * stride + (e % NC)] -= acc[e];
+  }
+}
+
 // one CTA (one warp) per span: diagonal block of the span + the rows below it, columns of this span only
 // (reference factor_spans_kernel, MatOpsCuda.cu:188-233)
 template <typename T>
@@ -457,12 +587,51 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
       B200_LAUNCH_CHECK();
     }
   };
-  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3)
+  // Measured on B200 (profiles/README.md, round 1): the staged (cooperative cp.async) kernel wins when every lane of
+  // the warp has a task in every iteration - the heavy destinations (stress workload, all heavy: 2.27 -> 1.78 ms) -
+  // and loses on the light list, where most destinations hold one or two tasks and the fixed cost of a cooperative
+  // iteration is paid for a few active lanes (BAL: 1.15 -> 1.94 ms). Default: direct loads for the light list, staged
+  // for the heavy list. BSPB200_GATHER=0: direct everywhere, 2: staged everywhere.
+  static const int mode = getenv("BSPB200_GATHER") ? atoi(getenv("BSPB200_GATHER")) : 1;
+  auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
+    static bool once = [&] {
+      B200_CUDA(cudaFuncSetAttribute(light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B200_CUDA(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      return true;
+    }();
+    (void)once;
+    constexpr int NT = kStagedWarps * 32;
+    if (plan.numLight > 0) {
+      if (mode == 2)
+        light<<<dim3(ceilDiv(plan.numLight * lanes, NT), 1, batch), NT, smem, st>>>(plan, data, plan.lightList, plan.numLight);
+      else
+        lightDirect<<<dim3(ceilDiv(plan.numLight * lanes, 128), 1, batch), 128, 0, st>>>(plan, data, plan.lightList, plan.numLight);
+      B200_LAUNCH_CHECK();
+    }
+    if (plan.numHeavy > 0) {
+      heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), NT, smem, st>>>(plan, data, plan.heavyList, plan.numHeavy);
+      B200_LAUNCH_CHECK();
+    }
+  };
+  const bool staged = mode != 0;
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
+    if (staged)
+      return fixedStaged(elim_gather_staged_kernel<T, 6, 6, 3, 8>, elim_gather_staged_kernel<T, 6, 6, 3, 128>,
+                         elim_gather_fixed_kernel<T, 6, 6, 3, 8>, 8, stagedSmemBytes<T, 6, 6, 3>());
     return fixed(elim_gather_fixed_kernel<T, 6, 6, 3, 8>, elim_gather_fixed_kernel<T, 6, 6, 3, 256>, 8);
-  if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
+  }
+  if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3) {
+    if (staged)
+      return fixedStaged(elim_gather_staged_kernel<T, 3, 3, 3, 4>, elim_gather_staged_kernel<T, 3, 3, 3, 128>,
+                         elim_gather_fixed_kernel<T, 3, 3, 3, 4>, 4, stagedSmemBytes<T, 3, 3, 3>());
     return fixed(elim_gather_fixed_kernel<T, 3, 3, 3, 4>, elim_gather_fixed_kernel<T, 3, 3, 3, 256>, 4);
-  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 6)
+  }
+  if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 6) {
+    if (staged)
+      return fixedStaged(elim_gather_staged_kernel<T, 6, 6, 6, 8>, elim_gather_staged_kernel<T, 6, 6, 6, 128>,
+                         elim_gather_fixed_kernel<T, 6, 6, 6, 8>, 8, stagedSmemBytes<T, 6, 6, 6>());
     return fixed(elim_gather_fixed_kernel<T, 6, 6, 6, 8>, elim_gather_fixed_kernel<T, 6, 6, 6, 256>, 8);
+  }
   int E = std::min(plan.maxDstElems, 256);
   int64_t threads = plan.numDst * E;
   elim_gather_kernel<T><<<dim3(ceilDiv(threads, 256), 1, batch), 256, 0, st>>>(plan, data, E);

@@ -41,6 +41,12 @@ int64_t bspb200_profile_report(char* json_out, int64_t cap) {
   return len;
 }
 
+int64_t bspb200_debug_read(int what, void* out, int64_t bytes) {
+  int64_t n = -1;
+  guarded([&] { n = BaSpaCho::b200::debugRead(what, out, bytes); });
+  return n;
+}
+
 int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                         const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int lower_only, void* stream) {
   return guarded([&] {

@@ -125,6 +125,10 @@ int bspb200_dev_potrf(int dtype, int64_t n, int64_t rows_below, void* A, int64_t
 int bspb200_profile_enable(int on);
 int64_t bspb200_profile_report(char* json_out, int64_t cap);
 
+/* diagnostics: what == 0 -> up to 64 clock64() phase stamps of CTA 0 of the last panel-kernel launch (only recorded
+ * when the environment variable BSPB200_PANEL_CLK=1 is set at first use); returns the bytes copied, < 0 on error */
+int64_t bspb200_debug_read(int what, void* out, int64_t bytes);
+
 /* number of kernel launches issued by this library since process start (bench.py "gpu_launches") */
 int64_t bspb200_launch_count(void);
 
