@@ -566,6 +566,227 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
 #undef B200_PCLK
 }
 
+// ------------------------------------------------------------------------------------------------ panel kernel v2
+// Same job as panel_kernel<T, true> (diagonal block + 64 rows below it per CTA), but the triangular solve no longer
+// runs as a second phase: the 64 slab rows are appended to the register-resident right-looking Cholesky as two more
+// row slots per thread (the factorization of a 160 x 96 trapezoid), so they are solved against every 4-column pivot
+// group in the same step, with the same two barriers, as the rows of the diagonal block. Measured on B200 (probe2,
+// profiles/): v1 spent 31.6k cycles in the Cholesky phase and 27.0k in the separate solve phase per panel; the slab
+// rows add FMA throughput only (no latency) to the former. The slab is prefetched with cp.async while the diagonal
+// block loads, the load counter of the writer protocol is not waited for, and both results leave through
+// shared-memory staging as coalesced row stores (v1: the writer CTA stored the factor column-wise, 7k cycles).
+constexpr int kP2Slots = 5;                  // row slots per thread: 3 (diagonal block) + 2 (slab)
+constexpr int kP2Rows = kNB + kPanelRows;    // 160
+constexpr int kP2LD = 97;                    // odd smem row stride: a warp walking down rows is conflict free
+
+template <int BYTES>
+__device__ __forceinline__ void cpAsyncZfill(uint32_t dst, const void* src, int srcBytes) {
+  if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(srcBytes));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(srcBytes));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPanelThreads, 1)
+    panel2_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl, Operand<T> Bop, int64_t ldb, const WavePanel* work,
+                  int* counters, int lumpsInLaunch, long long* clk) {
+#define B200_PCLK(i) \
+  if (clk && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.z == 0) clk[i] = clock64();
+  B200_PCLK(0)
+  constexpr int NW = kPanelThreads / 32;  // 8 warps
+  constexpr int R = kPanelRows;           // 64 slab rows per CTA
+  constexpr int RA = kP2Slots, CU = kNB / NW, LA = kNB / NW, LU = kNB / 32;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* S = reinterpret_cast<T*>(smemRaw);  // [kNB][kP2LD] diagonal block staging (in and out)
+  T* Xs = S + kNB * kP2LD;               // [R][kP2LD]   slab staging (in and out)
+  T* colbuf = Xs + R * kP2LD;            // [4][kP2Rows] raw columns of the current 4-column group
+  T* ybuf = colbuf + 4 * kP2Rows;        // [kNB][4]     finished rows of the group: L[i][j0 .. j0+3]
+  __shared__ int writerFlag;
+  T* __restrict__ L = Lop.at(blockIdx.z);
+  T* __restrict__ B = Bop.at(blockIdx.z);
+  int slab = blockIdx.x, lumpIdx = 0;
+  if (work) {  // batched over a work list (wavefront): one item = (lump column, 64-row slab)
+    const WavePanel w = work[blockIdx.x];
+    n = w.n, rows = w.rows, slab = w.slab, lumpIdx = w.lumpIdx;
+    L += w.dataOff;
+    B = L + (int64_t)n * n;
+    ldl = ldb = n;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = (int64_t)slab * R;
+  const int nr = (int)max((int64_t)0, min((int64_t)R, rows - r0));
+
+  // slab rows -> Xs (zero filled outside nr x n), in flight while the diagonal block is fetched
+#pragma unroll
+  for (int j = 0; j < R * kNB / kPanelThreads; j++) {
+    const int i = tid + kPanelThreads * j, r = i / kNB, c = i - r * kNB;
+    const bool ok = r < nr && c < n;
+    cpAsyncZfill<sizeof(T)>(smemAddr(Xs + r * kP2LD + c), ok ? B + (r0 + r) * ldb + c : B, ok ? (int)sizeof(T) : 0);
+  }
+  cpAsyncCommit();
+  {  // lower triangle -> S (coalesced, every load in flight at once; S is zeroed meanwhile)
+    T tmp[LA * LU];
+#pragma unroll
+    for (int a = 0; a < LA; a++)
+#pragma unroll
+      for (int u = 0; u < LU; u++) {
+        const int r = warp + NW * a, c = lane + 32 * u;
+        tmp[a * LU + u] = (c <= r && r < n) ? L[(int64_t)r * ldl + c] : T(0);
+      }
+    for (int i = tid; i < kNB * kP2LD; i += kPanelThreads) S[i] = T(0);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < LA; a++)
+#pragma unroll
+      for (int u = 0; u < LU; u++) {
+        const int r = warp + NW * a, c = lane + 32 * u;
+        if (c <= r && r < n) S[r * kP2LD + c] = tmp[a * LU + u];
+      }
+  }
+  cpAsyncWait<0>();
+  __syncthreads();
+  B200_PCLK(1)
+  // Writer protocol as in panel_kernel: every CTA of a lump column factors the diagonal block from the ORIGINAL values,
+  // so the CTA that counts itself in last (every other one provably holds its copy) writes the factor back. The
+  // result is only needed at the end of the kernel: nobody waits for the atomic here.
+  if (tid == 0) {
+    const int slabs = max(1, (int)((rows + R - 1) / R));
+    int* ctr = counters + (int64_t)blockIdx.z * lumpsInLaunch + lumpIdx;
+    __threadfence();
+    const int old = atomicAdd(ctr, 1);
+    writerFlag = (old == slabs - 1);
+    if (old == slabs - 1) *ctr = 0;
+  }
+  // thread (warp w, lane l): rows l + 32 a (a < 3: diagonal block, a = 3, 4: slab rows l + 32 (a - 3)), cols w + 8 u
+  T reg[RA][CU];
+#pragma unroll
+  for (int a = 0; a < RA; a++)
+#pragma unroll
+    for (int u = 0; u < CU; u++)
+      reg[a][u] = a < 3 ? S[(lane + 32 * a) * kP2LD + warp + NW * u] : Xs[(lane + 32 * (a - 3)) * kP2LD + warp + NW * u];
+  B200_PCLK(2)
+#pragma unroll
+  for (int u = 0; u < CU; u++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int j0 = NW * u + 4 * h;
+      if (j0 < n) {
+        const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
+        if (q >= 0 && q < 4) {
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (a >= 3 || lane + 32 * a >= j0) colbuf[q * kP2Rows + lane + 32 * a] = reg[a][u];
+        }
+        __syncthreads();
+        // pivot block d[r][c] = entry (j0 + r, j0 + c), r >= c; columns beyond n act as identity
+        T d[4][4], raw[RA][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+          for (int r = c; r < 4; r++) d[r][c] = colbuf[c * kP2Rows + j0 + r];
+#pragma unroll
+        for (int a = 0; a < RA; a++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) raw[a][c] = colbuf[c * kP2Rows + lane + 32 * a];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (j0 + c >= n) d[c][c] = T(1);
+        T rs[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+          for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
+          rs[c] = rsqrt(d[c][c]);
+#pragma unroll
+          for (int r = c + 1; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
+            d[r][c] *= rs[c];
+          }
+        }
+        // own rows: y = raw * D^-T (entries above the diagonal of the pivot block and finished rows -> 0)
+        T y[RA][4];
+#pragma unroll
+        for (int a = 0; a < RA; a++) {
+          const int t = a < 3 ? lane + 32 * a - j0 : kP2Rows;  // row index relative to the group (slab rows: below)
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            T v = raw[a][c];
+#pragma unroll
+            for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
+            y[a][c] = (t >= c) ? v * rs[c] : T(0);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+          if (warp == a) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
+          }
+        __syncthreads();
+        // rank-4 update of the columns after the group
+#pragma unroll
+        for (int u2 = u; u2 < CU; u2++) {
+          const Vec2<T> lo = load2(ybuf + (warp + NW * u2) * 4), hi = load2(ybuf + (warp + NW * u2) * 4 + 2);
+          T yc[4] = {lo.v[0], lo.v[1], hi.v[0], hi.v[1]};
+          if (u2 == u && !(h == 0 && warp >= 4)) {  // this slot's column is inside (or before) the group: no update
+#pragma unroll
+            for (int c = 0; c < 4; c++) yc[c] = T(0);
+          }
+#pragma unroll
+          for (int a = 0; a < RA; a++) {
+            // a < 3: some row of the slot is below the group (warp uniform) and the tile touches the lower triangle
+            if (a >= 3 || (j0 + 3 < 32 * a + 31 && NW * u2 <= 32 * a + 31)) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) reg[a][u2] -= y[a][c] * yc[c];
+            }
+          }
+        }
+        if (q >= 0 && q < 4) {
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (a >= 3 || lane + 32 * a >= j0)
+              reg[a][u] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+        }
+      }
+    }
+  }
+  B200_PCLK(3)
+  // results -> staging (lanes walk down rows: conflict free with the odd stride) -> coalesced row stores
+  __syncthreads();
+  const bool writer = writerFlag != 0;
+#pragma unroll
+  for (int a = 0; a < RA; a++)
+#pragma unroll
+    for (int u = 0; u < CU; u++) {
+      if (a < 3) {
+        if (writer) S[(lane + 32 * a) * kP2LD + warp + NW * u] = reg[a][u];
+      } else {
+        Xs[(lane + 32 * (a - 3)) * kP2LD + warp + NW * u] = reg[a][u];
+      }
+    }
+  __syncthreads();
+  B200_PCLK(4)
+  if (writer) {
+#pragma unroll 4
+    for (int r = warp; r < n; r += NW)
+#pragma unroll
+      for (int u = 0; u < LU; u++) {
+        const int c = lane + 32 * u;
+        if (c <= r) L[(int64_t)r * ldl + c] = S[r * kP2LD + c];
+      }
+  }
+  for (int r = warp; r < nr; r += NW)
+#pragma unroll
+    for (int u = 0; u < LU; u++) {
+      const int c = lane + 32 * u;
+      if (c < n) B[(r0 + r) * ldb + c] = Xs[r * kP2LD + c];
+    }
+  B200_PCLK(5)
+#undef B200_PCLK
+}
+
 // algorithmic flops of C = A B^T (lower-only: entries with col <= row)
 double gemmFlops(int64_t m, int64_t n, int64_t k, bool lowerOnly) {
   double elems = (double)m * n;
@@ -618,7 +839,19 @@ void gemmNT<double>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k,
                    ((uintptr_t)B.base % 16 == 0);
   // big tiles when they fill the machine, small ones for skinny / small products
   static const int cfg = getenv("BSPB200_GEMM_CFG") ? atoi(getenv("BSPB200_GEMM_CFG")) : 1;
-  if (m >= 96 && n >= 96 && (int64_t)ceilDiv(m, 128) * ceilDiv(n, 128) * batch >= 96) {
+  // 128 x 64 tiles that are actually computed (lower-only launches skip the tiles above the diagonal)
+  auto bigTiles = [&]() -> int64_t {
+    const int64_t tm = ceilDiv(m, 128), tn = ceilDiv(n, 64);
+    if (!lowerOnly) return tm * tn;
+    int64_t t = 0;
+    for (int64_t i = 0; i < tm; i++) t += std::min<int64_t>(tn, (i * 128 + 127) / 64 + 1);
+    return t;
+  };
+  // the big tiles need about 1.5 CTAs per SM to keep the DMMA pipes busy (one 4-warp CTA alone on an SM stalls on its
+  // own fragment loads: 1194^2 x 1248 lower-only = 105 big tiles ran at 9 TF/s, probe2); below that the 64 x 64 tiles
+  // (8 warps) spread the same work over all SMs
+  static const int64_t minBig = getenv("BSPB200_GEMM_MINBIG") ? atoi(getenv("BSPB200_GEMM_MINBIG")) : 222;
+  if (m >= 96 && n >= 64 && bigTiles() * batch >= minBig) {
     if (cfg == 1)  // 128 x 64 tiles, 4 warps, 3 stages: two CTAs per SM (finer tail, epilogue/main-loop overlap)
       launchGemmF64<128, 64, 16, 64, 32, 3>(st, batch, s, alpha, A, B, beta, C, aligned16);
     else
@@ -685,14 +918,32 @@ int64_t debugRead(int what, void* out, int64_t bytes) {
   return 0;
 }
 
+// BSPB200_PANEL=1 selects the two-phase panel kernel (v1) for the fused potrf + trsm launches; default v2
+static int panelVersion() {
+  static const int v = getenv("BSPB200_PANEL") ? atoi(getenv("BSPB200_PANEL")) : 2;
+  return v;
+}
+template <typename T>
+static size_t panel2Smem() {
+  return ((size_t)kNB * kP2LD + (size_t)kPanelRows * kP2LD + 4 * kP2Rows + 4 * kNB) * sizeof(T);
+}
+
 template <typename T, bool DO_POTRF>
 static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                         int64_t ldb) {
   if (n > kNB) throw std::runtime_error("panel kernel: block too large");
+  int ctas = std::max(1, ceilDiv(rows, kPanelRows));
+  if (DO_POTRF && panelVersion() == 2) {
+    static bool once2 = (setSmem(panel2_kernel<T>, panel2Smem<T>()), true);
+    (void)once2;
+    panel2_kernel<T><<<dim3(ctas, 1, batch), kPanelThreads, panel2Smem<T>(), st>>>(
+        n, rows, L, ldl, B, ldb, nullptr, panelCounters(batch), 1, panelClockBuf());
+    B200_LAUNCH_CHECK();
+    return;
+  }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
   static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
   (void)once;
-  int ctas = std::max(1, ceilDiv(rows, kPanelRows));
   panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr,
                                                                                panelCounters(batch), 1, panelClockBuf());
   B200_LAUNCH_CHECK();
@@ -704,10 +955,18 @@ void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const Wave
                          int numLumps, double flops) {
   if (count <= 0) return;
   static_assert(WavePlan::kPanelRows == kPanelRows, "slab size of the plan and of the kernel differ");
+  ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
+  if (panelVersion() == 2) {
+    static bool once2 = (setSmem(panel2_kernel<T>, panel2Smem<T>()), true);
+    (void)once2;
+    panel2_kernel<T><<<dim3((unsigned)count, 1, batch), kPanelThreads, panel2Smem<T>(), st>>>(
+        0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
+    B200_LAUNCH_CHECK();
+    return;
+  }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
   static bool once = (setSmem(panel_kernel<T, true>, smem), true);
   (void)once;
-  ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
   panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(
       0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
   B200_LAUNCH_CHECK();

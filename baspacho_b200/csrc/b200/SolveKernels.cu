@@ -457,6 +457,13 @@ __global__ void __launch_bounds__(kInvThreads, 1)
     }
   }
 
+  // Programmatic dependent launch: everything above reads only the factor and the block inverses, which no kernel of
+  // the solve writes, so a step launched with the PDL attribute runs its prologue while the previous step is still
+  // executing; from here on it touches the right-hand sides, which the previous step updates -> wait for it, then let
+  // the next step start its own prologue. (Without the launch attribute both instructions are no-ops.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   for (int g0 = 0; g0 < nRHS; g0 += kInvRHS) {
     const int ng = min(kInvRHS, nRHS - g0);
     for (int i = tid; i < kInvRHS * kTB; i += kInvThreads) {
@@ -593,11 +600,28 @@ __global__ void copy_vec_kernel(int64_t n, int nRHS, Operand<T> Xop, int64_t ldx
   Cop.at(blockIdx.z)[c * ldc + r] = Xop.at(blockIdx.z)[c * ldx + r];
 }
 
+// launch of one inverse-based block step; pdl: programmatic dependent launch on the previous kernel of the stream
+// (only for a step whose predecessor in the stream is the previous step of the same solve)
+template <typename T, bool TR>
+static void launchStepInv(cudaStream_t st, dim3 grid, bool pdl, int64_t n, int64_t j0, int jb, Operand<T> L, int64_t ldl,
+                          Operand<T> C, int64_t ldc, Operand<T> X, int64_t ldx, int nRHS, Operand<T> W) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(kInvThreads, 1, 1), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, solve_step_inv_kernel<T, TR>, n, j0, jb, L, ldl, C, ldc, X, ldx, nRHS, W));
+}
+
 template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
              bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady) {
   if (n <= 0 || nRHS <= 0) return;
   const int nb = kTB;
+  // BSPB200_PDL=0 disables the programmatic dependent launches; profiling (events between the steps) does too
+  static const bool pdlEnv = !(getenv("BSPB200_PDL") && atoi(getenv("BSPB200_PDL")) == 0);
+  const bool pdl = pdlEnv && !profileEnabled();
   if (n <= nb) {  // a single block: solved in place
     trsvBlock<T>(st, batch, (int)n, L, ldl, C, ldc, nRHS, transposed);
     return;
@@ -629,8 +653,8 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
       ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * rb * jb) * nRHS * batch,
                      (double)(jb * (jb + 1) / 2 + rb * jb) * sizeof(T) * batch);
       if (useInv)
-        solve_step_inv_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kInvThreads, 0, st>>>(
-            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch);
+        launchStepInv<T, false>(st, dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), pdl && j0 > 0, n, j0, (int)jb, L,
+                                ldl, C, ldc, scratch, ldx, nRHS, invScratch);
       else
         solve_step_kernel<T, false><<<dim3(std::max(1, ceilDiv(rb, kStepRows)), 1, batch), kTrsvWarps * 32, smem, st>>>(
             n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch, false);
@@ -642,8 +666,8 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
       ProfScope prof(st, KC_SOLVE_DENSE, (double)(jb * jb + 2.0 * j0 * jb) * nRHS * batch,
                      (double)(jb * (jb + 1) / 2 + j0 * jb) * sizeof(T) * batch);
       if (useInv)
-        solve_step_inv_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kInvThreads, 0, st>>>(
-            n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch);
+        launchStepInv<T, true>(st, dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), pdl && j0 + nb < n, n, j0, (int)jb,
+                               L, ldl, C, ldc, scratch, ldx, nRHS, invScratch);
       else
         solve_step_kernel<T, true><<<dim3(std::max(1, ceilDiv(j0, kStepCols)), 1, batch), kTrsvWarps * 32, smem, st>>>(
             n, j0, (int)jb, L, ldl, C, ldc, scratch, ldx, nRHS, invScratch, false);

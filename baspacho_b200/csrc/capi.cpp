@@ -13,6 +13,8 @@ namespace {
 
 struct HostStaging {
   BaSpaCho::b200::DevBuf<unsigned char> data, vec;
+  bool scanned = false;
+  std::vector<std::pair<int64_t, int64_t>> wide;  // (data offset, width) of the wide diagonal blocks, ascending
 };
 
 }  // namespace
@@ -91,7 +93,36 @@ int bspb200_factor_solve_host(bspb200_solver* s, int dtype, const void* host_dat
     const size_t dataBytes = (size_t)sv.dataSize() * es, vecBytes = (size_t)ld * std::max(0, n_rhs) * es;
     stg->data.ensure(dataBytes);
     stg->vec.ensure(std::max<size_t>(vecBytes, 1));
-    B200_CUDA(cudaMemcpyAsync(stg->data.ptr(), host_data, dataBytes, cudaMemcpyHostToDevice, st));
+    // The upper triangle of a diagonal block is don't-care on input (reference CoalescedBlockMatrix.h: only the
+    // lower triangle of a lump's diagonal block is meaningful), so wide diagonal blocks go up in row bands that stop
+    // at the diagonal: the 5226-wide camera lump of the BAL-shaped problem is 218 MB as a square, 114 MB as bands.
+    {
+      const auto& sk = sv.skel();
+      const char* src = (const char*)host_data;
+      char* dst = (char*)stg->data.ptr();
+      constexpr int64_t kMinWidth = 512, kBand = 256;
+      int64_t cursor = 0;
+      auto flat = [&](int64_t from, int64_t to) {
+        if (to > from)
+          B200_CUDA(cudaMemcpyAsync(dst + from * es, src + from * es, (size_t)(to - from) * es, cudaMemcpyHostToDevice, st));
+      };
+      if (!stg->scanned) {
+        for (int64_t l = 0; l < sk.numLumps(); l++)
+          if (sk.lumpSize(l) >= kMinWidth) stg->wide.emplace_back(sk.lumpDataOffset(l), sk.lumpSize(l));
+        stg->scanned = true;
+      }
+      for (const auto& ow : stg->wide) {
+        const int64_t off = ow.first, w = ow.second;
+        flat(cursor, off);
+        for (int64_t b0 = 0; b0 < w; b0 += kBand) {
+          const int64_t b1 = std::min(w, b0 + kBand);
+          B200_CUDA(cudaMemcpy2DAsync(dst + (off + b0 * w) * es, (size_t)w * es, src + (off + b0 * w) * es, (size_t)w * es,
+                                      (size_t)b1 * es, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+        }
+        cursor = off + w * w;
+      }
+      flat(cursor, sv.dataSize());
+    }
     if (n_rhs > 0) B200_CUDA(cudaMemcpyAsync(stg->vec.ptr(), host_vec, vecBytes, cudaMemcpyHostToDevice, st));
     if (dtype == 0) {
       sv.factor((double*)stg->data.ptr());

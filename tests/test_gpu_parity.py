@@ -269,6 +269,31 @@ def test_factor_solve_host_end_to_end():
     assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
 
 
+def test_host_end_to_end_wide_lump_and_heavy_destinations():
+    """BA-shaped problem whose camera part is one 600-wide lump (the host entry point uploads wide diagonal blocks in row
+    bands that stop at the diagonal) and whose diagonal camera blocks collect > 512 pair tasks each (the staged,
+    whole-CTA gather kernel of the sparse elimination), checked against the oracle and against A x = b."""
+    n_pts, n_cams = 14000, 140
+    sizes, ptrs, inds = H.ba_problem(n_pts, n_cams, seed=11, window=20)
+    g, o = make_pair(sizes, ptrs, inds, [0, n_pts], computation_model=_capi.MODEL_B200)
+    assert np.diff(g.lumpStart).max() >= 512
+    data = H.make_data(g, 5, np.float64, 1.2)
+    rhs = H.oapi().random_data_array(g.order, -1, 1, 38).reshape(1, g.order)
+    x = rhs.copy()
+    fac = np.empty_like(data)
+    g.factor_solve_host(data, x, fac)
+    ref, xr = data.copy(), rhs.copy()
+    o.factor(ref)
+    o.solve(ref, xr)
+    mask = np.tril(g.densify(np.ones_like(data))) > 0
+    assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(x - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+    # device-pointer path on the same problem (elimination + blocked dense factorization of the wide lump)
+    d = torch_of(data)
+    g.factor(d)
+    assert np.abs(g.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("model", [_capi.MODEL_B200, _capi.MODEL_OPENBLAS_I7])
 def test_grid_wide_and_small_lumps(model):
     """GRID family (Bench.cpp:322-343 genGrid): wide supernodes with rows below (blocked trapezoid Cholesky, GEMM+assemble
