@@ -105,8 +105,10 @@ ElimPlan buildElimPlan(const CoalescedBlockMatrixSkel& sk, int64_t lumpsBegin, i
     for (int64_t bRel : touched) perB[bRel] = 0;
     if (run >= (int64_t(1) << 31)) throw std::runtime_error("B200 sparse elimination plan: too many block pairs");
   }
-  for (int64_t d = 0; d < p.numDst(); d++)
-    (p.dstTaskPtr[d + 1] - p.dstTaskPtr[d] > ElimPlan::kHeavyTasks ? p.heavyList : p.lightList).push_back((int32_t)d);
+  for (int64_t d = 0; d < p.numDst(); d++) {
+    const int32_t nt = p.dstTaskPtr[d + 1] - p.dstTaskPtr[d];
+    (nt > ElimPlan::kHeavyTasks ? p.heavyList : p.lightList).push_back((int32_t)d);
+  }
   if (p.numDst() > 0) {
     p.uniRows = p.dstRows[0], p.uniCols = p.dstCols[0], p.uniK = p.taskK.empty() ? 0 : p.taskK[0];
     for (int64_t d = 0; d < p.numDst(); d++)

@@ -43,6 +43,11 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// entry of a kernel of the programmatic-dependent-launch chain (see launchChain)
+#define B200_CHAIN_ENTRY()                                           \
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    \
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
 struct GemmShape {
   int64_t m, n, k, lda, ldb, ldc;
   int lowerOnly;
@@ -60,6 +65,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   constexpr int LDS = BK + 4;
   constexpr int TM = WM / 8, TN = WN / 8;
   extern __shared__ __align__(16) double smemD[];
+  B200_CHAIN_ENTRY()
   double* As = smemD;
   double* Bs = smemD + STAGES * BM * LDS;
 
@@ -587,12 +593,13 @@ __device__ __forceinline__ void cpAsyncZfill(uint32_t dst, const void* src, int 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(srcBytes));
 }
 
-template <typename T>
+template <typename T, int UF>
 __global__ void __launch_bounds__(kPanelThreads, 1)
     panel2_kernel(int n, int64_t rows, Operand<T> Lop, int64_t ldl, Operand<T> Bop, int64_t ldb, const WavePanel* work,
                   int* counters, int lumpsInLaunch, long long* clk) {
 #define B200_PCLK(i) \
   if (clk && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.z == 0) clk[i] = clock64();
+  B200_CHAIN_ENTRY()
   B200_PCLK(0)
   constexpr int NW = kPanelThreads / 32;  // 8 warps
   constexpr int R = kPanelRows;           // 64 slab rows per CTA
@@ -666,106 +673,125 @@ __global__ void __launch_bounds__(kPanelThreads, 1)
     for (int u = 0; u < CU; u++)
       reg[a][u] = a < 3 ? S[(lane + 32 * a) * kP2LD + warp + NW * u] : Xs[(lane + 32 * (a - 3)) * kP2LD + warp + NW * u];
   B200_PCLK(2)
+  // Column loop: UF column slots (2 UF four-column steps) are unrolled per iteration, then the finished columns go to
+  // the shared-memory staging and the remaining slots shift down by UF, so that register indices stay static while
+  // the loop body stays small. (Fully unrolled - UF = 12, 340 KB of code - the kernel spent 55 % of its issue slots
+  // waiting for instruction fetch: ncu stall_no_inst, profiles/.) During iteration u0, slot s holds column
+  // warp + 8 (u0 + s).
+#pragma unroll 1
+  for (int u0 = 0; u0 < CU; u0 += UF) {
+    const int rem = CU - u0;  // live slots
 #pragma unroll
-  for (int u = 0; u < CU; u++) {
+    for (int uu = 0; uu < UF; uu++) {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int j0 = NW * u + 4 * h;
-      if (j0 < n) {
-        const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
-        if (q >= 0 && q < 4) {
+      for (int h = 0; h < 2; h++) {
+        const int j0 = NW * (u0 + uu) + 4 * h;
+        if (j0 < n) {
+          const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (a >= 3 || lane + 32 * a >= j0) colbuf[q * kP2Rows + lane + 32 * a] = reg[a][uu];
+          }
+          __syncthreads();
+          // pivot block d[r][c] = entry (j0 + r, j0 + c), r >= c; columns beyond n act as identity
+          T d[4][4], raw[RA][4];
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = c; r < 4; r++) d[r][c] = colbuf[c * kP2Rows + j0 + r];
 #pragma unroll
           for (int a = 0; a < RA; a++)
-            if (a >= 3 || lane + 32 * a >= j0) colbuf[q * kP2Rows + lane + 32 * a] = reg[a][u];
-        }
-        __syncthreads();
-        // pivot block d[r][c] = entry (j0 + r, j0 + c), r >= c; columns beyond n act as identity
-        T d[4][4], raw[RA][4];
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++) raw[a][c] = colbuf[c * kP2Rows + lane + 32 * a];
 #pragma unroll
-          for (int r = c; r < 4; r++) d[r][c] = colbuf[c * kP2Rows + j0 + r];
-#pragma unroll
-        for (int a = 0; a < RA; a++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) raw[a][c] = colbuf[c * kP2Rows + lane + 32 * a];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          if (j0 + c >= n) d[c][c] = T(1);
-        T rs[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-#pragma unroll
-          for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
-          rs[c] = rsqrt(d[c][c]);
-#pragma unroll
-          for (int r = c + 1; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
-            d[r][c] *= rs[c];
-          }
-        }
-        // own rows: y = raw * D^-T (entries above the diagonal of the pivot block and finished rows -> 0)
-        T y[RA][4];
-#pragma unroll
-        for (int a = 0; a < RA; a++) {
-          const int t = a < 3 ? lane + 32 * a - j0 : kP2Rows;  // row index relative to the group (slab rows: below)
+          for (int c = 0; c < 4; c++)
+            if (j0 + c >= n) d[c][c] = T(1);
+          T rs[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            T v = raw[a][c];
 #pragma unroll
-            for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
-            y[a][c] = (t >= c) ? v * rs[c] : T(0);
-          }
-        }
+            for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
+            rs[c] = rsqrt(d[c][c]);
 #pragma unroll
-        for (int a = 0; a < 3; a++)
-          if (warp == a) {
+            for (int r = c + 1; r < 4; r++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
-          }
-        __syncthreads();
-        // rank-4 update of the columns after the group
-#pragma unroll
-        for (int u2 = u; u2 < CU; u2++) {
-          const Vec2<T> lo = load2(ybuf + (warp + NW * u2) * 4), hi = load2(ybuf + (warp + NW * u2) * 4 + 2);
-          T yc[4] = {lo.v[0], lo.v[1], hi.v[0], hi.v[1]};
-          if (u2 == u && !(h == 0 && warp >= 4)) {  // this slot's column is inside (or before) the group: no update
-#pragma unroll
-            for (int c = 0; c < 4; c++) yc[c] = T(0);
-          }
-#pragma unroll
-          for (int a = 0; a < RA; a++) {
-            // a < 3: some row of the slot is below the group (warp uniform) and the tile touches the lower triangle
-            if (a >= 3 || (j0 + 3 < 32 * a + 31 && NW * u2 <= 32 * a + 31)) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) reg[a][u2] -= y[a][c] * yc[c];
+              for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
+              d[r][c] *= rs[c];
             }
           }
-        }
-        if (q >= 0 && q < 4) {
+          // own rows: y = raw * D^-T (entries above the diagonal of the pivot block and finished rows -> 0)
+          T y[RA][4];
 #pragma unroll
-          for (int a = 0; a < RA; a++)
-            if (a >= 3 || lane + 32 * a >= j0)
-              reg[a][u] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+          for (int a = 0; a < RA; a++) {
+            const int t = a < 3 ? lane + 32 * a - j0 : kP2Rows;  // row index relative to the group (slab rows: below)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              T v = raw[a][c];
+#pragma unroll
+              for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
+              y[a][c] = (t >= c) ? v * rs[c] : T(0);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+            if (warp == a) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
+            }
+          __syncthreads();
+          // rank-4 update of the columns after the group (slot sl = column warp + 8 (u0 + sl))
+#pragma unroll
+          for (int sl = uu; sl < CU; sl++) {
+            if (UF == CU || sl < rem) {
+              const int cb = NW * (u0 + sl);  // first column of the slot's 8-column block
+              const Vec2<T> lo = load2(ybuf + (warp + cb) * 4), hi = load2(ybuf + (warp + cb) * 4 + 2);
+              T yc[4] = {lo.v[0], lo.v[1], hi.v[0], hi.v[1]};
+              if (sl == uu && !(h == 0 && warp >= 4)) {  // this slot's column is inside (or before) the group: no update
+#pragma unroll
+                for (int c = 0; c < 4; c++) yc[c] = T(0);
+              }
+#pragma unroll
+              for (int a = 0; a < RA; a++) {
+                // a < 3: some row of the slot is below the group (warp uniform) and the tile touches the lower triangle
+                if (a >= 3 || (j0 + 3 < 32 * a + 31 && cb <= 32 * a + 31)) {
+#pragma unroll
+                  for (int c = 0; c < 4; c++) reg[a][sl] -= y[a][c] * yc[c];
+                }
+              }
+            }
+          }
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (a >= 3 || lane + 32 * a >= j0)
+                reg[a][uu] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+          }
         }
       }
+    }
+    // columns warp + 8 (u0 .. u0 + UF - 1) are final: stage them (lanes walk down rows: conflict free with the odd
+    // stride), then shift the slots
+#pragma unroll
+    for (int uu = 0; uu < UF; uu++)
+#pragma unroll
+      for (int a = 0; a < RA; a++) {
+        if (a < 3)
+          S[(lane + 32 * a) * kP2LD + warp + NW * (u0 + uu)] = reg[a][uu];
+        else
+          Xs[(lane + 32 * (a - 3)) * kP2LD + warp + NW * (u0 + uu)] = reg[a][uu];
+      }
+    if (UF < CU) {
+#pragma unroll
+      for (int sl = 0; sl + UF < CU; sl++)
+        if (sl + UF < rem) {
+#pragma unroll
+          for (int a = 0; a < RA; a++) reg[a][sl] = reg[a][sl + UF];
+        }
     }
   }
   B200_PCLK(3)
-  // results -> staging (lanes walk down rows: conflict free with the odd stride) -> coalesced row stores
-  __syncthreads();
   const bool writer = writerFlag != 0;
-#pragma unroll
-  for (int a = 0; a < RA; a++)
-#pragma unroll
-    for (int u = 0; u < CU; u++) {
-      if (a < 3) {
-        if (writer) S[(lane + 32 * a) * kP2LD + warp + NW * u] = reg[a][u];
-      } else {
-        Xs[(lane + 32 * (a - 3)) * kP2LD + warp + NW * u] = reg[a][u];
-      }
-    }
   __syncthreads();
   B200_PCLK(4)
   if (writer) {
@@ -803,6 +829,28 @@ void setSmem(KernelT kernel, size_t bytes) {
     B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+// Programmatic dependent launch of the dense-factorization chain (panel -> trailing GEMM -> panel ...): every kernel
+// of the chain releases its dependents at once and then waits for its predecessor (griddepcontrol at the top of the
+// kernel), so the next kernel's CTAs are already resident when the last wave of the current one drains; the data
+// dependence is carried by the wait. Opt-in (see chainPdl); an active profiler (events between launches) turns it off.
+static bool chainPdl() {
+  // measured on the BAL-shaped benchmark (round 1): factor 5.92 ms without, 6.04 ms with the chain -> off unless
+  // BSPB200_PDL_CHAIN=1 (the early-resident CTAs of the next kernel take SM slots from the running one); the
+  // solve steps, whose prologue is independent of the previous step, keep their PDL (SolveKernels.cu)
+  static const bool env = getenv("BSPB200_PDL_CHAIN") && atoi(getenv("BSPB200_PDL_CHAIN")) != 0;
+  return env && !profileEnabled();
+}
+template <typename... KArgs, typename... Args>
+static void launchChain(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(threads, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = chainPdl() ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 template <int BM, int BN, int BK, int WM, int WN, int STAGES>
 void launchGemmF64(cudaStream_t st, int batch, const GemmShape& s, double alpha, Operand<double> A, Operand<double> B,
                    double beta, Operand<double> C, bool aligned16) {
@@ -813,12 +861,12 @@ void launchGemmF64(cudaStream_t st, int batch, const GemmShape& s, double alpha,
     auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 2>;
     static bool once = (setSmem(kern, smem), true);
     (void)once;
-    kern<<<grid, NT, smem, st>>>(s, alpha, A, B, beta, C);
+    launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
   } else {
     auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 1>;
     static bool once = (setSmem(kern, smem), true);
     (void)once;
-    kern<<<grid, NT, smem, st>>>(s, alpha, A, B, beta, C);
+    launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
   }
   B200_LAUNCH_CHECK();
 }
@@ -928,17 +976,40 @@ static size_t panel2Smem() {
   return ((size_t)kNB * kP2LD + (size_t)kPanelRows * kP2LD + 4 * kP2Rows + 4 * kNB) * sizeof(T);
 }
 
+// column slots unrolled per loop iteration of panel2_kernel (BSPB200_PANEL_UF: 1, 2, 3, 4, 6 or 12 = fully unrolled)
+static int panelUF() {
+  static const int v = getenv("BSPB200_PANEL_UF") ? atoi(getenv("BSPB200_PANEL_UF")) : 12;
+  return v;
+}
+template <typename T, int UF>
+static void launchPanel2UF(cudaStream_t st, dim3 grid, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
+                           int64_t ldb, const WavePanel* work, int* counters, int lumpsInLaunch, long long* clk) {
+  static bool once = (setSmem(panel2_kernel<T, UF>, panel2Smem<T>()), true);
+  (void)once;
+  launchChain(panel2_kernel<T, UF>, grid, kPanelThreads, panel2Smem<T>(), st, n, rows, L, ldl, B, ldb, work, counters,
+              lumpsInLaunch, clk);
+  B200_LAUNCH_CHECK();
+}
+template <typename T>
+static void launchPanel2(cudaStream_t st, dim3 grid, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
+                         int64_t ldb, const WavePanel* work, int* counters, int lumpsInLaunch, long long* clk) {
+  switch (panelUF()) {
+    case 1: return launchPanel2UF<T, 1>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+    case 2: return launchPanel2UF<T, 2>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+    case 3: return launchPanel2UF<T, 3>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+    case 4: return launchPanel2UF<T, 4>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+    case 6: return launchPanel2UF<T, 6>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+    default: return launchPanel2UF<T, 12>(st, grid, n, rows, L, ldl, B, ldb, work, counters, lumpsInLaunch, clk);
+  }
+}
+
 template <typename T, bool DO_POTRF>
 static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                         int64_t ldb) {
   if (n > kNB) throw std::runtime_error("panel kernel: block too large");
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
   if (DO_POTRF && panelVersion() == 2) {
-    static bool once2 = (setSmem(panel2_kernel<T>, panel2Smem<T>()), true);
-    (void)once2;
-    panel2_kernel<T><<<dim3(ctas, 1, batch), kPanelThreads, panel2Smem<T>(), st>>>(
-        n, rows, L, ldl, B, ldb, nullptr, panelCounters(batch), 1, panelClockBuf());
-    B200_LAUNCH_CHECK();
+    launchPanel2<T>(st, dim3(ctas, 1, batch), n, rows, L, ldl, B, ldb, nullptr, panelCounters(batch), 1, panelClockBuf());
     return;
   }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
@@ -957,11 +1028,8 @@ void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const Wave
   static_assert(WavePlan::kPanelRows == kPanelRows, "slab size of the plan and of the kernel differ");
   ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
   if (panelVersion() == 2) {
-    static bool once2 = (setSmem(panel2_kernel<T>, panel2Smem<T>()), true);
-    (void)once2;
-    panel2_kernel<T><<<dim3((unsigned)count, 1, batch), kPanelThreads, panel2Smem<T>(), st>>>(
-        0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
-    B200_LAUNCH_CHECK();
+    launchPanel2<T>(st, dim3((unsigned)count, 1, batch), 0, 0, data, 0, data, 0, work,
+                    panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
     return;
   }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);

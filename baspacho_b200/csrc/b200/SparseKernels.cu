@@ -591,7 +591,9 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // the warp has a task in every iteration - the heavy destinations (stress workload, all heavy: 2.27 -> 1.78 ms) -
   // and loses on the light list, where most destinations hold one or two tasks and the fixed cost of a cooperative
   // iteration is paid for a few active lanes (BAL: 1.15 -> 1.94 ms). Default: direct loads for the light list, staged
-  // for the heavy list. BSPB200_GATHER=0: direct everywhere, 2: staged everywhere.
+  // for the heavy list. BSPB200_GATHER=0: direct everywhere, 2: staged everywhere. (A third variant - cooperative
+  // coalesced ld.global into registers, then the stage - was measured slower on both workloads, BAL 1.92 ms and
+  // stress 3.4 ms, and was removed: profiles/README.md.)
   static const int mode = getenv("BSPB200_GATHER") ? atoi(getenv("BSPB200_GATHER")) : 1;
   auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
     static bool once = [&] {
