@@ -581,6 +581,19 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_kernel(int n, int64_t 
 // rows add FMA throughput only (no latency) to the former. The slab is prefetched with cp.async while the diagonal
 // block loads, the load counter of the writer protocol is not waited for, and both results leave through
 // shared-memory staging as coalesced row stores (v1: the writer CTA stored the factor column-wise, 7k cycles).
+// 1 / sqrt(x) without the slow-path branch of rsqrt(double): hardware seed (MUFU.RSQ64H, ~2^-22 relative error over the
+// whole exponent range) + two Newton steps y <- y (1.5 - 0.5 x y^2), straight-line code on the critical path of every
+// pivot. A non-positive pivot yields NaN / Inf, which propagates into the factor exactly like sqrt() of it would.
+__device__ __forceinline__ double rsqrtFast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ float rsqrtFast(float x) { return rsqrtf(x); }
+
 constexpr int kP2Slots = 5;                  // row slots per thread: 3 (diagonal block) + 2 (slab)
 constexpr int kP2Rows = kNB + kPanelRows;    // 160
 constexpr int kP2LD = 97;                    // odd smem row stride: a warp walking down rows is conflict free
@@ -703,7 +716,8 @@ __global__ void __launch_bounds__(kPanelThreads, 1)
 #pragma unroll
           for (int a = 0; a < RA; a++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) raw[a][c] = colbuf[c * kP2Rows + lane + 32 * a];
+            for (int c = 0; c < 4; c++)
+              raw[a][c] = (UF == CU && a < 3 && 32 * a + 31 < j0) ? T(0) : colbuf[c * kP2Rows + lane + 32 * a];
 #pragma unroll
           for (int c = 0; c < 4; c++)
             if (j0 + c >= n) d[c][c] = T(1);
@@ -712,7 +726,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1)
           for (int c = 0; c < 4; c++) {
 #pragma unroll
             for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
-            rs[c] = rsqrt(d[c][c]);
+            rs[c] = rsqrtFast(d[c][c]);
 #pragma unroll
             for (int r = c + 1; r < 4; r++) {
 #pragma unroll
@@ -725,6 +739,11 @@ __global__ void __launch_bounds__(kPanelThreads, 1)
 #pragma unroll
           for (int a = 0; a < RA; a++) {
             const int t = a < 3 ? lane + 32 * a - j0 : kP2Rows;  // row index relative to the group (slab rows: below)
+            if (UF == CU && a < 3 && 32 * a + 31 < j0) {  // every row of the slot is finished (static when unrolled)
+#pragma unroll
+              for (int c = 0; c < 4; c++) y[a][c] = T(0);
+              continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               T v = raw[a][c];

@@ -316,9 +316,16 @@ def run_b200(args):
     dgemm_peak = measure_dgemm_peak(torch, dev)
     g = prof["gemm"]
     gemm_tf = g["flops"] / max(g["ms"], 1e-9) / 1e9
+    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture (never measured under a profiler
+    # here); per launch, averaged over the captured launches like `achieved` is averaged over the step's launches
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if args.workload == "bal" and os.path.exists(tpath):
+        tj = json.load(open(tpath))["gemm_nt_f64_kernel"]
+        traffic, traffic_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("source", "launches", "largest_launch")}
     roofline = {"kernel": "gemm_nt_f64_kernel (DMMA m8n8k4 SYRK/GEMM tiles of the blocked supernode Cholesky)",
                 "bound": "tensor", "achieved": gemm_tf, "peak": dgemm_peak, "unit": "TFLOP/s",
-                "frac": gemm_tf / dgemm_peak if dgemm_peak else None, "traffic": None,
+                "frac": gemm_tf / dgemm_peak if dgemm_peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json holds no fp64 figure; "
                                "tcgen05 has no f64 kind, DMMA is the fp64 tensor path)",
                 "launches_per_step": g["launches"], "share_of_step_ms": g["ms"]}
