@@ -62,6 +62,10 @@ void trsmBlock(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, in
 template <typename T>
 void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld);
 
+// load counters used by the panel launches issued from this host thread until reset with nullptr (`batch` zeroed ints;
+// needed when lump columns are factored concurrently on several streams)
+void setPanelCounters(int* counters);
+
 // diagonal Cholesky + triangular solve of many small lump columns in one launch (work list on the device)
 struct WavePanel;
 template <typename T>

@@ -70,6 +70,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
     if (const char* e = getenv("BSPB200_WAVEFRONT")) useWavefront = atoi(e) != 0;
     if (const char* e = getenv("BSPB200_INVERSE_SOLVE")) useInverseSolve = atoi(e) != 0;
+    if (const char* e = getenv("BSPB200_LANES")) numLanes = std::max(1, std::min(8, atoi(e)));
     // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
     potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
     solveSparseLStat.enabled = solveSparseLtStat.enabled = pseudoFactorStat.enabled = symmStat.enabled = false;
@@ -171,6 +172,46 @@ struct B200SymbolicCtx : SymbolicCtx {
       wave = std::move(w);
     }
     return *wave;
+  }
+
+  // ---- lanes: side streams on which independent wide lumps of one tree level are factored concurrently
+  struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf<int64_t> spanToChainOffset;
+    DevBuf<int> counters;
+  };
+  std::vector<Lane> lanes;
+  cudaEvent_t evLevel = nullptr;
+  DevBuf<unsigned char> laneScratch;
+  int numLanes = 4;
+  void ensureLanes(int batch, size_t tempBytesPerLane) {
+    if (lanes.empty()) {
+      lanes.resize(numLanes);
+      for (Lane& ln : lanes) {
+        B200_CUDA(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        ln.spanToChainOffset.resize(std::max<int64_t>(1, skel.numSpans()));
+      }
+      B200_CUDA(cudaEventCreateWithFlags(&evLevel, cudaEventDisableTiming));
+    }
+    for (Lane& ln : lanes)
+      if (ln.counters.size() < (size_t)batch) {
+        B200_CUDA(cudaStreamSynchronize(ln.st));
+        ln.counters.resize(batch);
+        B200_CUDA(cudaMemset(ln.counters.ptr(), 0, batch * sizeof(int)));
+      }
+    if (laneScratch.size() < tempBytesPerLane * lanes.size()) {
+      for (Lane& ln : lanes) B200_CUDA(cudaStreamSynchronize(ln.st));
+      laneScratch.resize(tempBytesPerLane * lanes.size());
+    }
+  }
+  ~B200SymbolicCtx() override {
+    for (Lane& ln : lanes) {
+      if (ln.st) cudaStreamDestroy(ln.st);
+      if (ln.done) cudaEventDestroy(ln.done);
+    }
+    if (evLevel) cudaEventDestroy(evLevel);
   }
 
   const CoalescedBlockMatrixSkel& skel;
@@ -318,6 +359,29 @@ struct B200NumericCtx : NumericCtx<TT> {
         waveUpdate<T>(sym.stream, m.batch, all, wv.tiles.ptr() + L.tileBegin, L.tileEnd - L.tileBegin,
                       wv.targets.ptr(), wv.sources.ptr(), wv.rowMap.ptr());
         static const int order = getenv("BSPB200_WAVE_ORDER") ? atoi(getenv("BSPB200_WAVE_ORDER")) : 0;
+        // the wide lumps of a level are independent of each other (and of the level's small lumps): with two or more
+        // of them, each runs its whole chain (updates from its sources, blocked factorization of its column) on its
+        // own lane - stream, GEMM temp, span-to-chain table, panel counters - between two joins with the main stream
+        const bool concurrent = sym.numLanes > 1 && L.bigLumps.size() >= 2 && !profileEnabled();
+        if (concurrent) {
+          sym.ensureLanes(m.batch, laneTempBytes());
+          const int used = (int)std::min<size_t>(sym.lanes.size(), L.bigLumps.size());
+          B200_CUDA(cudaEventRecord(sym.evLevel, sym.stream));
+          for (int k = 0; k < used; k++) B200_CUDA(cudaStreamWaitEvent(sym.lanes[k].st, sym.evLevel, 0));
+          for (size_t i = 0; i < L.bigLumps.size(); i++) {
+            const int k = (int)(i % used);
+            LaneCtx lc = laneCtx(k);
+            updateLump(m, L.bigLumps[i], firstSrc, upToLump, &lc);
+            factorLumpColumn(m, L.bigLumps[i], &lc);
+          }
+          potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
+                                 L.numSmall, wv.panelFlops[lv]);
+          for (int k = 0; k < used; k++) {
+            B200_CUDA(cudaEventRecord(sym.lanes[k].done, sym.lanes[k].st));
+            B200_CUDA(cudaStreamWaitEvent(sym.stream, sym.lanes[k].done, 0));
+          }
+          continue;
+        }
         if (order == 0)
           for (int64_t l : L.bigLumps) updateLump(m, l, firstSrc, upToLump);
         potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
@@ -335,14 +399,38 @@ struct B200NumericCtx : NumericCtx<TT> {
     }
   }
 
+  // where one lump column's chain of kernels runs: the solver's stream and shared workspaces, or a lane
+  struct LaneCtx {
+    cudaStream_t st;
+    Work<T> temp;
+    int64_t* spanToChainOffset;
+    int* counters;
+  };
+  size_t laneTempBytes() const { return (size_t)std::max<int64_t>(1, tempSize) * batch * sizeof(T); }
+  LaneCtx laneCtx(int k) {
+    LaneCtx lc;
+    lc.st = sym.lanes[k].st;
+    lc.temp.base = (T*)(sym.laneScratch.ptr() + (size_t)k * laneTempBytes());
+    lc.temp.stride = tempSize;
+    lc.spanToChainOffset = sym.lanes[k].spanToChainOffset.ptr();
+    lc.counters = sym.lanes[k].counters.ptr();
+    return lc;
+  }
+
   // contributions of the already factored sources [firstSrc, min(l, upToLump)) into lump l: GEMM into the temp + scatter
-  void updateLump(const Mats<T>& m, int64_t l, int64_t firstSrc, int64_t upToLump) {
+  void updateLump(const Mats<T>& m, int64_t l, int64_t firstSrc, int64_t upToLump, const LaneCtx* lc = nullptr) {
+    cudaStream_t st = lc ? lc->st : sym.stream;
+    int64_t* s2c = lc ? lc->spanToChainOffset : sym.spanToChainOffset.ptr();
     bool prepared = false;
     for (int64_t r = skel.boardRowPtr[l], rEnd = skel.boardRowPtr[l + 1] - 1; r < rEnd; r++) {
       const int64_t src = skel.boardColLump[r];
       if (src >= upToLump) break;
       if (src < firstSrc) continue;
-      if (!prepared) prepareAssemble(l), prepared = true;
+      if (!prepared) {
+        const int64_t begin = skel.chainColPtr[l];
+        b200::prepareAssemble(st, sym.dsk, s2c, begin, skel.chainColPtr[l + 1] - begin);
+        prepared = true;
+      }
       const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
       const int64_t k = skel.lumpSize(src);
       const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
@@ -352,16 +440,18 @@ struct B200NumericCtx : NumericCtx<TT> {
       const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
       BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
       Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
-      gemmNT<T>(sym.stream, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(temp(), 0), rowsInBoard,
-                false);
-      b200::assemble<T>(sym.stream, m.batch, sym.dsk, sym.spanToChainOffset.ptr(), m, temp(), rowBegin,
-                        skel.lumpSize(l), cb + ch0, rowsInBoard, chEnd - ch0, ch1 - ch0, rowsToEnd);
+      const Work<T> tmp = lc ? lc->temp : temp();
+      gemmNT<T>(st, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(tmp, 0), rowsInBoard, false);
+      b200::assemble<T>(st, m.batch, sym.dsk, s2c, m, tmp, rowBegin, skel.lumpSize(l), cb + ch0, rowsInBoard,
+                        chEnd - ch0, ch1 - ch0, rowsToEnd);
     }
   }
 
-  void factorLumpColumn(const Mats<T>& m, int64_t l) {
+  void factorLumpColumn(const Mats<T>& m, int64_t l, const LaneCtx* lc = nullptr) {
     const int64_t n = skel.lumpSize(l);
-    potrfTrapezoid<T>(sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
+    if (lc) setPanelCounters(lc->counters);
+    potrfTrapezoid<T>(lc ? lc->st : sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
+    if (lc) setPanelCounters(nullptr);
   }
 
   B200SymbolicCtx& sym;

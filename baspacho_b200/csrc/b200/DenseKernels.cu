@@ -56,8 +56,8 @@ struct GemmShape {
 // ------------------------------------------------------------------------------------------------ fp64 DMMA GEMM
 // CTA tile BM x BN x BK, warp tile WM x WN built from m8n8k4 DMMA tiles; A and B tiles are both K-contiguous
 // ([row][k] with a 4-double pad: the quad-strided fragment loads are bank-conflict free).
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, int VEC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int VEC, int MINB = 1>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
     gemm_nt_f64_kernel(GemmShape s, double alpha, Operand<double> Aop, Operand<double> Bop, double beta,
                        Operand<double> Cop) {
   constexpr int NWN = BN / WN;
@@ -870,19 +870,19 @@ static void launchChain(void (*kernel)(KArgs...), dim3 grid, int threads, size_t
   B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB = 1>
 void launchGemmF64(cudaStream_t st, int batch, const GemmShape& s, double alpha, Operand<double> A, Operand<double> B,
                    double beta, Operand<double> C, bool aligned16) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   size_t smem = (size_t)STAGES * (BM + BN) * (BK + 4) * sizeof(double);
   dim3 grid(ceilDiv(s.n, BN), ceilDiv(s.m, BM), batch);
   if (aligned16) {
-    auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 2>;
+    auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 2, MINB>;
     static bool once = (setSmem(kern, smem), true);
     (void)once;
     launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
   } else {
-    auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 1>;
+    auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 1, MINB>;
     static bool once = (setSmem(kern, smem), true);
     (void)once;
     launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
@@ -919,7 +919,13 @@ void gemmNT<double>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k,
   // (8 warps) spread the same work over all SMs
   static const int64_t minBig = getenv("BSPB200_GEMM_MINBIG") ? atoi(getenv("BSPB200_GEMM_MINBIG")) : 222;
   if (m >= 96 && n >= 64 && bigTiles() * batch >= minBig) {
-    if (cfg == 1)  // 128 x 64 tiles, 4 warps, 3 stages: two CTAs per SM (finer tail, epilogue/main-loop overlap)
+    // Same tile with 2 stages and registers capped for THREE CTAs per SM (444 slots instead of 296): measured better
+    // exactly when it makes every tile resident at once (2442^2 x 1152 lower-only, 419 tiles: 0.355 -> 0.298 ms;
+    // 4266 x 672 x 288: 0.107 -> 0.089 ms) and worse otherwise (3594^2 x 1632, 1653 tiles: 0.731 -> 0.780 ms).
+    const int64_t tiles = bigTiles() * batch;
+    if (cfg == 3 || (cfg == 1 && tiles > 2 * 148 && tiles <= 3 * 148))
+      launchGemmF64<128, 64, 16, 64, 32, 2, 3>(st, batch, s, alpha, A, B, beta, C, aligned16);
+    else if (cfg == 1)  // 128 x 64 tiles, 4 warps, 3 stages: two CTAs per SM (finer tail, epilogue/main-loop overlap)
       launchGemmF64<128, 64, 16, 64, 32, 3>(st, batch, s, alpha, A, B, beta, C, aligned16);
     else
       launchGemmF64<128, 128, 16, 64, 32, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
@@ -950,6 +956,10 @@ int maxBlockDim<float>() {
 }
 
 // zero-initialised load counters of the panel kernel (grow-only; the kernel leaves them zero again)
+// per-lane override of the load counters (concurrent lump columns on different streams must not share them):
+// set by the caller around potrfTrapezoid; the buffer holds `batch` zero-initialised ints and is left zeroed
+static thread_local int* tlsPanelCtr = nullptr;
+void setPanelCounters(int* counters) { tlsPanelCtr = counters; }
 static int* panelCounters(int64_t needed) {
   static int* buf = nullptr;
   static int64_t cap = 0;
@@ -1028,14 +1038,16 @@ static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand
   if (n > kNB) throw std::runtime_error("panel kernel: block too large");
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
   if (DO_POTRF && panelVersion() == 2) {
-    launchPanel2<T>(st, dim3(ctas, 1, batch), n, rows, L, ldl, B, ldb, nullptr, panelCounters(batch), 1, panelClockBuf());
+    launchPanel2<T>(st, dim3(ctas, 1, batch), n, rows, L, ldl, B, ldb, nullptr,
+                    tlsPanelCtr ? tlsPanelCtr : panelCounters(batch), 1, panelClockBuf());
     return;
   }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
   static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
   (void)once;
   panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr,
-                                                                               panelCounters(batch), 1, panelClockBuf());
+                                                                               tlsPanelCtr ? tlsPanelCtr : panelCounters(batch),
+                                                                               1, panelClockBuf());
   B200_LAUNCH_CHECK();
 }
 
