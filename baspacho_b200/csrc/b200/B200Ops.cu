@@ -70,7 +70,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
     if (const char* e = getenv("BSPB200_WAVEFRONT")) useWavefront = atoi(e) != 0;
     if (const char* e = getenv("BSPB200_INVERSE_SOLVE")) useInverseSolve = atoi(e) != 0;
-    if (const char* e = getenv("BSPB200_LANES")) numLanes = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("BSPB200_LANES")) numLanes = std::max(1, std::min(16, atoi(e)));
     // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
     potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
     solveSparseLStat.enabled = solveSparseLtStat.enabled = pseudoFactorStat.enabled = symmStat.enabled = false;
@@ -184,7 +184,7 @@ struct B200SymbolicCtx : SymbolicCtx {
   std::vector<Lane> lanes;
   cudaEvent_t evLevel = nullptr;
   DevBuf<unsigned char> laneScratch;
-  int numLanes = 4;
+  int numLanes = 8;
   void ensureLanes(int batch, size_t tempBytesPerLane) {
     if (lanes.empty()) {
       lanes.resize(numLanes);
