@@ -86,23 +86,50 @@ void trsmAny(cudaStream_t st, int batch, int64_t n, int64_t rows, Operand<T> L, 
 
 // ---------------------------------------------------------------------------------- vectors (SolveKernels.cu)
 // Vectors are column-major (rows x nRHS, leading dimension ldc).
+
+// one 96 x 96 diagonal block whose inverse the dense solves use: where it sits in the factor data and in the scratch
+struct InvBlockDesc {
+  int64_t dataOff;  // element offset of the block's (0,0) entry in the factor data
+  int64_t wOff;     // element offset of its 2 x 96 x 96 slot (W, W^T) in the inverse scratch
+  int32_t ld, jb;   // leading dimension (= lump width) and block size (<= 96)
+};
+// W = L_bb^-1 for every block of the list, one launch (the blocks of all wide lumps of a factor)
+template <typename T>
+void invertBlockList(cudaStream_t st, int batch, const InvBlockDesc* list, int64_t count, Operand<T> data,
+                     Operand<T> invScratch);
+
+// state of the chained triangular solve (trsv_chain_kernel): the device exchange buffer of self-validating
+// {value, epoch} slots + the arrival ticket, and the host-side running epoch / ticket values of the launches issued so
+// far (one stream, launches in order)
+struct ChainSync {
+  void* xbuf = nullptr;        // uint4 [batch][blocksPerItem][rhsCap][96], zeroed once (epoch 0 is never used)
+  unsigned* ticket = nullptr;  // never reset
+  unsigned epoch = 0, ticketBase = 0;
+  int blocksPerItem = 0, rhsCap = 0;
+};
+
 // tril(L) X = C (transposed=false) or tril(L)^T X = C (transposed=true), L n x n row-major (ldl), any n
 template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
              bool transposed, Operand<T> scratch /* n x nRHS per batch item, used when n > one block */,
              Operand<T> invScratch /* optional: 2 x 96 x 96 x ceil(n / 96) per batch item -> inverse-based block steps */,
-             bool inversesReady = false /* the scratch already holds the inverses of this matrix */);
+             bool inversesReady = false /* the scratch already holds the inverses of this matrix */,
+             ChainSync* chain = nullptr /* with invScratch: one flag-chained launch instead of one launch per block */);
 
 // out[i * outRowStride + c * outColStride] (+)= alpha * sum_q M[i][q] * X[c * ldx + q]   (M rows x cols, ldm)
 // (tmp row-major rows x nRHS: strides (nRHS, 1); a column-major vector: strides (1, ld))
 template <typename T>
 void gemvRows(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm, Operand<T> X,
-              int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate);
+              int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate,
+              const int64_t* rowMap = nullptr /* device: output row of every M row (scatter = fused assembleVec) */);
 
 // X[c * ldx + q] += alpha * sum_i M[i][q] * in[i * inRowStride + c * inColStride]
 template <typename T>
 void gemvColsT(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm,
-               Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS);
+               Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS,
+               Operand<T> part = Operand<T>() /* optional scratch for row-chunk partial sums (tall panels) */,
+               int64_t partCapacity = 0 /* elements per batch item */,
+               const int64_t* rowMap = nullptr /* device: input row of every M row (gather = fused assembleVecT) */);
 
 // y(col-major ldy)[0..n) += alpha * sym(M) * x(col-major ldx)[0..n), M n x n lower-stored row-major (ldm = n)
 template <typename T>

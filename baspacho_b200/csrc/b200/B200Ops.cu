@@ -70,6 +70,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     spanToChainOffset.resize(std::max<int64_t>(1, s.numSpans()));
     if (const char* e = getenv("BSPB200_WAVEFRONT")) useWavefront = atoi(e) != 0;
     if (const char* e = getenv("BSPB200_INVERSE_SOLVE")) useInverseSolve = atoi(e) != 0;
+    if (const char* e = getenv("BSPB200_CHAIN_SOLVE")) useChainSolve = atoi(e) != 0;
     if (const char* e = getenv("BSPB200_LANES")) numLanes = std::max(1, std::min(16, atoi(e)));
     // per-op timers insert a device sync after every op: off unless Solver::enableStats() asks for them
     potrfStat.enabled = trsmStat.enabled = sygeStat.enabled = asmblStat.enabled = false;
@@ -213,6 +214,92 @@ struct B200SymbolicCtx : SymbolicCtx {
     }
     if (evLevel) cudaEventDestroy(evLevel);
   }
+
+  // ---- dense solves: slots of the 96 x 96 block inverses of every lump wider than one block (built once), the work
+  // list of the one-launch inversion, and the flag/ticket state of the flag-chained triangular solve
+  static constexpr int64_t kInvBlock = 96;
+  struct InvPlan {
+    int64_t total = 0;                                       // scratch elements per batch item
+    std::map<int64_t, std::pair<int64_t, int64_t>> slot;     // diagonal block offset -> (scratch offset, width)
+    DevBuf<InvBlockDesc> list;
+    int64_t count = 0, maxBlocks = 0;
+  };
+  std::unique_ptr<InvPlan> invPlanPtr;
+  const InvPlan& invPlan() {
+    if (!invPlanPtr) {
+      auto p = std::make_unique<InvPlan>();
+      const int64_t minBlocks = useChainSolve ? 2 : 6;  // per-step launches: narrow lumps keep the substitution steps
+      vector<InvBlockDesc> descs;
+      for (int64_t l = 0; l < skel.numLumps(); l++) {
+        const int64_t w = skel.lumpSize(l), nblk = (w + kInvBlock - 1) / kInvBlock;
+        if (nblk < minBlocks) continue;
+        const int64_t off = skel.lumpDataOffset(l);
+        p->slot[off] = {p->total, w};
+        for (int64_t b = 0; b < nblk; b++)
+          descs.push_back(InvBlockDesc{off + b * kInvBlock * w + b * kInvBlock, p->total + b * 2 * kInvBlock * kInvBlock,
+                                       (int32_t)w, (int32_t)std::min(kInvBlock, w - b * kInvBlock)});
+        p->total += 2 * kInvBlock * kInvBlock * nblk;
+        p->maxBlocks = std::max(p->maxBlocks, nblk);
+      }
+      p->count = (int64_t)descs.size();
+      p->list.upload(descs);
+      invPlanPtr = std::move(p);
+    }
+    return *invPlanPtr;
+  }
+  // vector row of every below-diagonal row of every dense lump (what assembleVec / assembleVecT look up chain by
+  // chain): lets the fused solves scatter / gather inside the gemv kernels
+  struct BelowRows {
+    vector<int64_t> ptr;  // per lump, offset into target (lumps of the elimination ranges: empty)
+    DevBuf<int64_t> target;
+  };
+  std::unique_ptr<BelowRows> belowRowsPtr;
+  const BelowRows& belowRows() {
+    if (!belowRowsPtr) {
+      auto p = std::make_unique<BelowRows>();
+      int64_t denseFrom = 0;
+      for (const B200SymElimCtx* e : elimRegistry) denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
+      vector<int64_t> tgt;
+      p->ptr.assign(skel.numLumps() + 1, 0);
+      for (int64_t l = 0; l < skel.numLumps(); l++) {
+        p->ptr[l] = (int64_t)tgt.size();
+        if (l < denseFrom) continue;
+        const int64_t cb = skel.chainColPtr[l], ord = skel.boardChainColOrd[skel.boardColPtr[l] + 1];
+        const int64_t numChains = skel.boardChainColOrd[skel.boardColPtr[l + 1] - 1];
+        for (int64_t ch = cb + ord; ch < cb + numChains; ch++) {
+          const int64_t span = skel.chainRowSpan[ch];
+          for (int64_t r = skel.spanStart[span]; r < skel.spanStart[span + 1]; r++) tgt.push_back(r);
+        }
+      }
+      p->ptr[skel.numLumps()] = (int64_t)tgt.size();
+      if (tgt.empty()) tgt.push_back(0);
+      p->target.upload(tgt);
+      belowRowsPtr = std::move(p);
+    }
+    return *belowRowsPtr;
+  }
+  ChainSync chain;
+  DevBuf<unsigned> chainTicket;
+  DevBuf<unsigned char> chainXbuf;
+  int chainBatch = 0;
+  ChainSync* chainSync(int batch, int nRHS) {
+    if (!useChainSolve) return nullptr;
+    const InvPlan& ip = invPlan();
+    if (ip.maxBlocks == 0) return nullptr;
+    if (batch > chainBatch || nRHS > chain.rhsCap) {
+      B200_CUDA(cudaStreamSynchronize(stream));
+      chainBatch = std::max(batch, chainBatch), chain.rhsCap = std::max(nRHS, chain.rhsCap);
+      chainXbuf.resize((size_t)chainBatch * ip.maxBlocks * chain.rhsCap * kInvBlock * 16);
+      B200_CUDA(cudaMemset(chainXbuf.ptr(), 0, chainXbuf.size()));  // tags 0: the epoch starts at 1 and only grows
+      if (!chainTicket.ptr()) {
+        chainTicket.resize(1);
+        B200_CUDA(cudaMemset(chainTicket.ptr(), 0, sizeof(unsigned)));
+      }
+      chain.xbuf = chainXbuf.ptr(), chain.ticket = chainTicket.ptr(), chain.blocksPerItem = (int)ip.maxBlocks;
+    }
+    return &chain;
+  }
+  bool useChainSolve = true;
 
   const CoalescedBlockMatrixSkel& skel;
   cudaStream_t stream = nullptr;
@@ -475,47 +562,105 @@ struct B200SolveCtx : SolveCtx<TT> {
   int64_t vecStride() const { return std::max<int64_t>(1, skel.order() * nRHS); }
   // block inverses of EVERY wide lump live side by side in the scratch (slot table by diagonal-block offset), so the
   // backward pass of solve() reuses what the forward pass computed
-  static constexpr int64_t kInvMinBlocks = 6;  // narrower lumps keep the substitution-based steps
-  void buildInvTable() {
-    if (invTotal >= 0) return;
-    invTotal = 0;
-    for (int64_t l = 0; l < skel.numLumps(); l++) {
-      int64_t w = skel.lumpSize(l), nblk = (w + 95) / 96;
-      if (nblk < kInvMinBlocks) continue;
-      invSlot[skel.lumpDataOffset(l)] = {invTotal, w};
-      invTotal += 2 * 96 * 96 * nblk;
-    }
-  }
-  T* scratchBase() {
-    buildInvTable();
-    return (T*)sym.scratch((size_t)(2 * vecStride() + invTotal) * batch * sizeof(T));
-  }
+  int64_t invTotal() { return sym.useInverseSolve ? sym.invPlan().total : 0; }
+  T* scratchBase() { return (T*)sym.scratch((size_t)(2 * vecStride() + invTotal()) * batch * sizeof(T)); }
   Work<T> temp(int which = 0) {
     Work<T> w;
     w.stride = vecStride();
     w.base = scratchBase() + (size_t)which * w.stride * batch;
     return w;
   }
+  Operand<T> invBase() {
+    Operand<T> o;
+    o.base = scratchBase() + (size_t)2 * vecStride() * batch;
+    o.bstride = invTotal();
+    return o;
+  }
   // scratch operand for the inverses of the lump whose diagonal block starts at offM (null operand: not eligible)
   Operand<T> invScratch(int64_t offM, int64_t n, bool* ready) {
     Operand<T> o;
     *ready = false;
-    buildInvTable();
-    auto it = invSlot.find(offM);
-    if (!sym.useInverseSolve || it == invSlot.end() || it->second.second != n) return o;
-    o.base = scratchBase() + (size_t)2 * vecStride() * batch + it->second.first;
-    o.bstride = invTotal;
-    *ready = invDone.count(offM) > 0;
+    if (!sym.useInverseSolve) return o;
+    const auto& slot = sym.invPlan().slot;
+    auto it = slot.find(offM);
+    if (it == slot.end() || it->second.second != n) return o;
+    o = invBase();
+    o.base += it->second.first;
+    *ready = invAll || invDone.count(offM) > 0;
     invDone.insert(offM);
     return o;
   }
-  int64_t invTotal = -1;
-  std::map<int64_t, std::pair<int64_t, int64_t>> invSlot;  // diagonal block offset -> (scratch offset, width)
-  std::set<int64_t> invDone;                               // inverses computed through this context
+  std::set<int64_t> invDone;  // inverses computed through this context
+  bool invAll = false;        // ... all of them, by the one-launch inversion
   const void* invData = nullptr;
   void invCheckData(const TT* data) {  // a context serves one factor; a different matrix invalidates the inverses
-    if (invData != (const void*)data) invDone.clear();
+    if (invData != (const void*)data) invDone.clear(), invAll = false;
     invData = data;
+  }
+  // all block inverses of the factor in ONE launch (instead of one serial 96-step launch per lump inside the chain)
+  void invertAll(const TT* data) {
+    invCheckData(data);
+    if (invAll || !sym.useInverseSolve) return;
+    const auto& ip = sym.invPlan();
+    if (ip.count > 0) {
+      Mats<T> m = mats.get(data, sym.stream);
+      invertBlockList<T>(sym.stream, m.batch, ip.list.ptr(), ip.count, opnd(m, 0), invBase());
+    }
+    invAll = true;
+  }
+
+  // ---- whole-range solves (MatOps.h addition): the sequence of Solver::internalSolveLRange / internalSolveLtRange
+  // (reference Solver.cpp:268-397) with every block inverse of the factor computed up front in one launch
+  bool hasFusedSolve() override { return true; }
+
+  void fusedSolveL(const TT* data, int64_t startLump, int64_t upToLump, TT* C, int64_t ldc) override {
+    int64_t denseFrom = 0;
+    for (const B200SymElimCtx* e : sym.elimRegistry) {
+      denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
+      if (e->dev.lumpsEnd > upToLump) return;
+      if (startLump > e->dev.lumpsBegin) continue;
+      sparseElimSolveL(*e, data, e->dev.lumpsBegin, e->dev.lumpsEnd, C, ldc);
+    }
+    denseFrom = std::max(denseFrom, startLump);
+    if (denseFrom < upToLump) invertAll(data);
+    for (int64_t l = denseFrom; l < upToLump; l++) {
+      const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
+      const int64_t off = skel.lumpDataOffset(l);
+      solveL(data, off, n, C, start, ldc);
+      if (rows == 0) continue;
+      // C[rows below] -= L21 x_l: gemv + assembleVec of the reference sequence in one kernel (scatter through the row table)
+      const auto& br = sym.belowRows();
+      BASPACHO_CHECK_EQ(br.ptr[l + 1] - br.ptr[l], rows);
+      Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+      gemvRows<T>(sym.stream, m.batch, rows, n, T(-1), opnd(m, off + n * n), n, opnd(v, start), ldc, opnd(v, 0), 1, ldc, nRHS,
+                  true, br.target.ptr() + br.ptr[l]);
+    }
+  }
+
+  void fusedSolveLt(const TT* data, int64_t startLump, int64_t upToLump, TT* C, int64_t ldc) override {
+    int64_t denseFrom = 0;
+    for (const B200SymElimCtx* e : sym.elimRegistry) denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
+    denseFrom = std::max(denseFrom, startLump);
+    if (denseFrom < upToLump) invertAll(data);
+    for (int64_t l = upToLump - 1; l >= denseFrom; l--) {
+      const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
+      const int64_t off = skel.lumpDataOffset(l);
+      if (rows > 0) {
+        // x_l -= L21^T C[rows below]: assembleVecT + gemvT in one product (gather through the row table)
+        const auto& br = sym.belowRows();
+        BASPACHO_CHECK_EQ(br.ptr[l + 1] - br.ptr[l], rows);
+        Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+        gemvColsT<T>(sym.stream, m.batch, rows, n, T(-1), opnd(m, off + n * n), n, opnd(v, 0), 1, ldc, opnd(v, start), ldc,
+                     nRHS, opnd(temp2(), 0), vecStride(), br.target.ptr() + br.ptr[l]);
+      }
+      solveLt(data, off, n, C, start, ldc);
+    }
+    for (int64_t r = (int64_t)sym.elimRegistry.size() - 1; r >= 0; r--) {
+      const B200SymElimCtx* e = sym.elimRegistry[r];
+      if (e->dev.lumpsEnd > upToLump) continue;
+      if (e->dev.lumpsBegin < startLump) return;
+      sparseElimSolveLt(*e, data, e->dev.lumpsBegin, e->dev.lumpsEnd, C, ldc);
+    }
   }
   Work<T> temp2() { return temp(1); }
 
@@ -554,7 +699,8 @@ struct B200SolveCtx : SolveCtx<TT> {
     invCheckData(data);
     bool ready = false;
     Operand<T> inv = invScratch(offM, n, &ready);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), inv, ready);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), inv, ready,
+               sym.chainSync(m.batch, nRHS));
   }
 
   void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
@@ -563,7 +709,8 @@ struct B200SolveCtx : SolveCtx<TT> {
     invCheckData(data);
     bool ready = false;
     Operand<T> inv = invScratch(offM, n, &ready);
-    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), inv, ready);
+    trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), inv, ready,
+               sym.chainSync(m.batch, nRHS));
   }
 
   void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,
@@ -579,7 +726,7 @@ struct B200SolveCtx : SolveCtx<TT> {
     auto timer = sym.solveGemvTStat.template instance<B200SyncOps>();
     Mats<T> m = mats.get(data, sym.stream), v = vecs.get(A, sym.stream);
     gemvColsT<T>(sym.stream, m.batch, nRows, nCols, alpha, opnd(m, offM), nCols, opnd(temp(), 0), nRHS, 1,
-                 opnd(v, offA), lda, nRHS);
+                 opnd(v, offA), lda, nRHS, opnd(temp2(), 0), vecStride());
   }
 
   int64_t rowsOfChains(int64_t chainColPtr, int64_t numColItems) const {

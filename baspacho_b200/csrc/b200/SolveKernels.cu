@@ -86,17 +86,32 @@ __global__ void __launch_bounds__(kTrsvWarps * 32) trsv_block_kernel(int n, Oper
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_rows_warp_kernel(int64_t rows, int64_t cols, T alpha, Operand<T> Mop,
                                                              int64_t ldm, Operand<T> Xop, int64_t ldx, Operand<T> Oop,
-                                                             int64_t ors, int64_t ocs, int nRHS, bool accumulate) {
+                                                             int64_t ors, int64_t ocs, int nRHS, bool accumulate,
+                                                             const int64_t* __restrict__ rowMap) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= rows) return;
   const T* __restrict__ m = Mop.at(blockIdx.z) + row * ldm;
   const T* __restrict__ X = Xop.at(blockIdx.z);
-  T* out = Oop.at(blockIdx.z) + row * ors;
+  T* out = Oop.at(blockIdx.z) + (rowMap ? rowMap[row] : row) * ors;  // rowMap: scatter (fused assembleVec)
   for (int c0 = 0; c0 < nRHS; c0 += 4) {
     T acc[4] = {0, 0, 0, 0};
     const int nc = min(4, nRHS - c0);
-    for (int64_t q = lane; q < cols; q += 32) {
+    int64_t q = lane;
+    for (; q + 224 < cols; q += 256) {  // 8 independent row loads in flight per lane (the loop is latency bound)
+      T mv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) mv[e] = m[q + 32 * e];
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++)
+        if (cc < nc) {
+          const T* xc = X + (int64_t)(c0 + cc) * ldx + q;
+          T p0 = mv[0] * xc[0] + mv[1] * xc[32], p1 = mv[2] * xc[64] + mv[3] * xc[96];
+          T p2 = mv[4] * xc[128] + mv[5] * xc[160], p3 = mv[6] * xc[192] + mv[7] * xc[224];
+          acc[cc] += (p0 + p1) + (p2 + p3);
+        }
+    }
+    for (; q < cols; q += 32) {
       T mv = m[q];
 #pragma unroll
       for (int cc = 0; cc < 4; cc++)
@@ -119,12 +134,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemv_rows_thread_kernel(int64_t rows, int64_t cols, T alpha, Operand<T> Mop,
                                                                int64_t ldm, Operand<T> Xop, int64_t ldx,
                                                                Operand<T> Oop, int64_t ors, int64_t ocs, int nRHS,
-                                                               bool accumulate) {
+                                                               bool accumulate, const int64_t* __restrict__ rowMap) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const T* __restrict__ m = Mop.at(blockIdx.z) + row * ldm;
   const T* __restrict__ X = Xop.at(blockIdx.z);
-  T* out = Oop.at(blockIdx.z) + row * ors;
+  T* out = Oop.at(blockIdx.z) + (rowMap ? rowMap[row] : row) * ors;
   for (int c = 0; c < nRHS; c++) {
     T acc = 0;
     for (int q = 0; q < cols; q++) acc += m[q] * X[(int64_t)c * ldx + q];
@@ -137,7 +152,8 @@ __global__ void __launch_bounds__(256) gemv_rows_thread_kernel(int64_t rows, int
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_cols_t_kernel(int64_t rows, int64_t cols, T alpha, Operand<T> Mop,
                                                           int64_t ldm, Operand<T> Iop, int64_t irs, int64_t ics,
-                                                          Operand<T> Xop, int64_t ldx, int nRHS) {
+                                                          Operand<T> Xop, int64_t ldx, int nRHS,
+                                                          const int64_t* __restrict__ rowMap) {
   __shared__ T red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t q = (int64_t)blockIdx.x * 32 + tx;
@@ -147,7 +163,8 @@ __global__ void __launch_bounds__(256) gemv_cols_t_kernel(int64_t rows, int64_t 
   for (int c = 0; c < nRHS; c++) {
     T acc = 0;
     if (q < cols)
-      for (int64_t r = ty; r < rows; r += 8) acc += M[r * ldm + q] * in[r * irs + (int64_t)c * ics];
+      for (int64_t r = ty; r < rows; r += 8)
+        acc += M[r * ldm + q] * in[(rowMap ? rowMap[r] : r) * irs + (int64_t)c * ics];  // rowMap: fused assembleVecT
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && q < cols) {
@@ -158,6 +175,57 @@ __global__ void __launch_bounds__(256) gemv_cols_t_kernel(int64_t rows, int64_t 
     }
     __syncthreads();
   }
+}
+
+// the same product split over row chunks (grid.y) so that tall panels fill the machine: pass 1 writes the partial
+// column sums of every chunk, pass 2 adds them in chunk order (deterministic) into X
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_t_part_kernel(int64_t rows, int64_t cols, Operand<T> Mop, int64_t ldm,
+                                                               Operand<T> Iop, int64_t irs, int64_t ics, Operand<T> Pop,
+                                                               int nRHS, int64_t rowsPerChunk,
+                                                               const int64_t* __restrict__ rowMap) {
+  __shared__ T red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t q = (int64_t)blockIdx.x * 32 + tx;
+  const T* __restrict__ M = Mop.at(blockIdx.z);
+  const T* __restrict__ in = Iop.at(blockIdx.z);
+  T* part = Pop.at(blockIdx.z) + (int64_t)blockIdx.y * nRHS * cols;
+  const int64_t r0 = (int64_t)blockIdx.y * rowsPerChunk, r1 = min(rows, r0 + rowsPerChunk);
+  for (int c = 0; c < nRHS; c++) {
+    T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (q < cols) {
+      int64_t r = r0 + ty;
+      for (; r + 24 < r1; r += 32) {
+        const T m0 = M[r * ldm + q], m1 = M[(r + 8) * ldm + q], m2 = M[(r + 16) * ldm + q], m3 = M[(r + 24) * ldm + q];
+        const int64_t i0 = rowMap ? rowMap[r] : r, i1 = rowMap ? rowMap[r + 8] : r + 8;
+        const int64_t i2 = rowMap ? rowMap[r + 16] : r + 16, i3 = rowMap ? rowMap[r + 24] : r + 24;
+        a0 += m0 * in[i0 * irs + (int64_t)c * ics], a1 += m1 * in[i1 * irs + (int64_t)c * ics];
+        a2 += m2 * in[i2 * irs + (int64_t)c * ics], a3 += m3 * in[i3 * irs + (int64_t)c * ics];
+      }
+      for (; r < r1; r += 8) a0 += M[r * ldm + q] * in[(rowMap ? rowMap[r] : r) * irs + (int64_t)c * ics];
+    }
+    red[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && q < cols) {
+      T tot = 0;
+#pragma unroll
+      for (int g = 0; g < 8; g++) tot += red[g][tx];
+      part[(int64_t)c * cols + q] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_t_reduce_kernel(int64_t cols, T alpha, Operand<T> Pop, int chunks,
+                                                                 Operand<T> Xop, int64_t ldx, int nRHS) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cols * nRHS) return;
+  const int64_t q = i % cols, c = i / cols;
+  const T* __restrict__ part = Pop.at(blockIdx.z);
+  T tot = 0;
+  for (int k = 0; k < chunks; k++) tot += part[((int64_t)k * nRHS + c) * cols + q];
+  Xop.at(blockIdx.z)[c * ldx + q] += alpha * tot;
 }
 
 template <typename T>
@@ -196,25 +264,42 @@ void trsvBlock(cudaStream_t st, int batch, int n, Operand<T> L, int64_t ldl, Ope
 
 template <typename T>
 void gemvRows(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm, Operand<T> X,
-              int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate) {
+              int64_t ldx, Operand<T> out, int64_t outRowStride, int64_t outColStride, int nRHS, bool accumulate,
+              const int64_t* rowMap) {
   if (rows <= 0 || nRHS <= 0) return;
   ProfScope prof(st, KC_SOLVE_DENSE, 2.0 * rows * cols * nRHS * batch, (double)rows * cols * sizeof(T) * batch);
   if (cols <= 16)
     gemv_rows_thread_kernel<T><<<dim3(ceilDiv(rows, 256), 1, batch), 256, 0, st>>>(
-        rows, cols, alpha, M, ldm, X, ldx, out, outRowStride, outColStride, nRHS, accumulate);
+        rows, cols, alpha, M, ldm, X, ldx, out, outRowStride, outColStride, nRHS, accumulate, rowMap);
   else
     gemv_rows_warp_kernel<T><<<dim3(ceilDiv(rows, 8), 1, batch), 256, 0, st>>>(
-        rows, cols, alpha, M, ldm, X, ldx, out, outRowStride, outColStride, nRHS, accumulate);
+        rows, cols, alpha, M, ldm, X, ldx, out, outRowStride, outColStride, nRHS, accumulate, rowMap);
   B200_LAUNCH_CHECK();
 }
 
 template <typename T>
 void gemvColsT(cudaStream_t st, int batch, int64_t rows, int64_t cols, T alpha, Operand<T> M, int64_t ldm,
-               Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS) {
+               Operand<T> in, int64_t inRowStride, int64_t inColStride, Operand<T> X, int64_t ldx, int nRHS,
+               Operand<T> part, int64_t partCapacity, const int64_t* rowMap) {
   if (rows <= 0 || cols <= 0 || nRHS <= 0) return;
   ProfScope prof(st, KC_SOLVE_DENSE, 2.0 * rows * cols * nRHS * batch, (double)rows * cols * sizeof(T) * batch);
+  // tall panel: split the rows over grid.y (about 4 CTAs per SM in total), partial sums through `part`
+  const int64_t colTiles = ceilDiv(cols, 32);
+  int64_t chunks = std::min<int64_t>({(592 + colTiles * batch - 1) / (colTiles * batch), (rows + 63) / 64,
+                                      part.base ? partCapacity / (cols * nRHS) : 0});
+  if (chunks >= 2) {
+    const int64_t rpc = ((rows + chunks - 1) / chunks + 7) / 8 * 8;
+    chunks = (rows + rpc - 1) / rpc;
+    gemv_cols_t_part_kernel<T><<<dim3((unsigned)colTiles, (unsigned)chunks, batch), 256, 0, st>>>(
+        rows, cols, M, ldm, in, inRowStride, inColStride, part, nRHS, rpc, rowMap);
+    B200_LAUNCH_CHECK();
+    gemv_cols_t_reduce_kernel<T><<<dim3(ceilDiv(cols * nRHS, 256), 1, batch), 256, 0, st>>>(cols, alpha, part, (int)chunks,
+                                                                                            X, ldx, nRHS);
+    B200_LAUNCH_CHECK();
+    return;
+  }
   gemv_cols_t_kernel<T><<<dim3(ceilDiv(cols, 32), 1, batch), 256, 0, st>>>(rows, cols, alpha, M, ldm, in, inRowStride,
-                                                                          inColStride, X, ldx, nRHS);
+                                                                          inColStride, X, ldx, nRHS, rowMap);
   B200_LAUNCH_CHECK();
 }
 
@@ -535,15 +620,11 @@ __global__ void __launch_bounds__(kInvThreads, 1)
 // computes column c of W by forward substitution (4 accumulators), W is written twice to the scratch, row-major
 // (slot 0) and transposed (slot 1), zero padded to 96 x 96 - the operands of the inverse-based block steps.
 template <typename T>
-__global__ void __launch_bounds__(128) invert_blocks_kernel(int64_t n, Operand<T> Lop, int64_t ldl, Operand<T> Wop) {
+__device__ __forceinline__ void invertBlockBody(const T* __restrict__ D, int64_t ldl, int jb, T* W) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   T* Ls = reinterpret_cast<T*>(smemRaw);  // [kTB][kTLD]
   T* Ws = Ls + kTB * kTLD;                // [kTB][kTLD]
   T* dinv = Ws + kTB * kTLD;              // [kTB]
-  const int64_t j0 = (int64_t)blockIdx.x * kTB;
-  const int jb = (int)min((int64_t)kTB, n - j0);
-  const T* __restrict__ D = Lop.at(blockIdx.z) + j0 * ldl + j0;
-  T* W = Wop.at(blockIdx.z) + (int64_t)blockIdx.x * (2 * kTB * kTB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 2 * kTB * kTLD + kTB; i += 128) Ls[i] = T(0);
   __syncthreads();
@@ -593,6 +674,213 @@ __global__ void __launch_bounds__(128) invert_blocks_kernel(int64_t n, Operand<T
 }
 
 template <typename T>
+__global__ void __launch_bounds__(128) invert_blocks_kernel(int64_t n, Operand<T> Lop, int64_t ldl, Operand<T> Wop) {
+  const int64_t j0 = (int64_t)blockIdx.x * kTB;
+  invertBlockBody<T>(Lop.at(blockIdx.z) + j0 * ldl + j0, ldl, (int)min((int64_t)kTB, n - j0),
+                     Wop.at(blockIdx.z) + (int64_t)blockIdx.x * (2 * kTB * kTB));
+}
+
+// the same for the diagonal blocks of MANY lumps in one launch (work list built once per skeleton)
+template <typename T>
+__global__ void __launch_bounds__(128) invert_blocks_list_kernel(const InvBlockDesc* __restrict__ list, Operand<T> Dop,
+                                                                   Operand<T> Wop) {
+  const InvBlockDesc d = list[blockIdx.x];
+  invertBlockBody<T>(Dop.at(blockIdx.z) + d.dataOff, d.ld, d.jb, Wop.at(blockIdx.z) + d.wOff);
+}
+
+// ---- chained dense triangular solve: ONE launch per lump and direction instead of one launch per 96-column step.
+// CTA i owns block row i (forward) / block column i (backward) of the triangle. It streams its off-diagonal 96 x 96
+// tiles in the order their solved blocks become available (register double buffer: the next tile is in flight while
+// the CTA waits), accumulates tile * x_j, and as soon as the last neighbour is published finishes
+// x_i = W_i (b_i - sum) with the precomputed block inverse (staged in shared memory at kernel start) and publishes it.
+// Publication is self-validating (the scheme of NCCL's LL protocol): every solved value is stored as two 8-byte words
+// {low half, tag} {high half, tag} with tag = the launch's epoch; 8-byte accesses are single-copy atomic, so a consumer
+// that reads both tags equal to the epoch holds the value - one L2 round trip from the producer's store to the
+// consumer's registers, no flag, no fence. Consumers poll with volatile loads (L2; L1 is never involved).
+// The critical path per block is that round trip + one tile product + one 96 x 96 matvec instead of a kernel boundary.
+// CTAs take their block from an arrival ticket, so a CTA only ever waits for CTAs that arrived before it (no deadlock
+// when the grid exceeds the resident capacity, e.g. batched solves). The exchange buffer is never reset: every launch
+// uses a fresh epoch, and every right-hand side has its own slots.
+constexpr int kChThreads = 256, kChWarps = 8, kChRows = kTB / kChWarps;  // 12 tile rows per warp
+
+__device__ __forceinline__ void chainPublish(uint4* slot, double v, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ void chainPublish(uint4* slot, float v, unsigned tag) {
+  chainPublish(slot, (double)v, tag);
+}
+template <typename T>
+__device__ __forceinline__ T chainAwait(const uint4* slot, unsigned tag) {
+  unsigned lo, t0, hi, t1;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
+                 : "l"(slot)
+                 : "memory");
+  } while (t0 != tag || t1 != tag);
+  return (T)__hiloint2double((int)hi, (int)lo);
+}
+
+template <typename T>
+__device__ __forceinline__ void chainLoadTile(T (&t)[kChRows][3], const T* __restrict__ L, int64_t ldl, int64_t r0,
+                                              int64_t c0, int64_t n, int warp, int lane) {
+#pragma unroll
+  for (int a = 0; a < kChRows; a++) {
+    const int64_t row = r0 + warp * kChRows + a;
+#pragma unroll
+    for (int u = 0; u < 3; u++) t[a][u] = (row < n) ? L[row * ldl + c0 + lane + 32 * u] : T(0);
+  }
+}
+
+template <typename T, bool TR, int NR>
+__global__ void __launch_bounds__(kChThreads, 1)
+    trsv_chain_kernel(int64_t n, int nbk, Operand<T> Lop, int64_t ldl, Operand<T> Cop, int64_t ldc, int nRHS,
+                      Operand<T> Wop, uint4* xbuf, int blocksPerItem, unsigned* ticket, unsigned ticketBase,
+                      unsigned epoch) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* Wsm = reinterpret_cast<T*>(smemRaw);  // [kTB][kTB] block inverse (transposed copy for the backward solve)
+  T* ys = Wsm + kTB * kTB;                 // [NR][kTB]  b_i - sum
+  T* part = ys + NR * kTB;                 // backward: [kChWarps][NR][kTB] partial column sums
+  __shared__ unsigned slotS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) slotS = atomicAdd(ticket, 1u) - ticketBase;
+  __syncthreads();
+  const unsigned slot = slotS;
+  const int item = (int)(slot / (unsigned)nbk), ord = (int)(slot % (unsigned)nbk);
+  const int i = TR ? nbk - 1 - ord : ord;
+  const T* __restrict__ L = Lop.at(item);
+  T* C = Cop.at(item);
+  const T* __restrict__ Wm = Wop.at(item) + (int64_t)i * (2 * kTB * kTB) + (TR ? kTB * kTB : 0);
+  // exchange slots of (item, block j, right-hand side c): xb + (j * nRHS + c) * kTB
+  uint4* xb = xbuf + (int64_t)item * blocksPerItem * nRHS * kTB;
+  const int64_t i0 = (int64_t)i * kTB;
+  const int ib = (int)min((int64_t)kTB, n - i0);
+  const int cnt = ord;  // off-diagonal tiles of this CTA; the s-th one belongs to block (TR ? nbk - 1 - s : s)
+  for (int idx = tid; idx < kTB * kTB; idx += kChThreads) Wsm[idx] = Wm[idx];
+
+  for (int g0 = 0; g0 < nRHS; g0 += NR) {
+    const int ng = min(NR, nRHS - g0);
+    T acc[NR];     // forward: lane a < 12 of warp w holds the sum of row 12 w + a
+    T pc[NR][3];   // backward: partial sums of columns lane + 32 u over the warp's rows
+#pragma unroll
+    for (int q = 0; q < NR; q++) acc[q] = pc[q][0] = pc[q][1] = pc[q][2] = T(0);
+
+    auto consume = [&](const T(&t)[kChRows][3], int s) {
+      const int j = TR ? nbk - 1 - s : s;
+      const uint4* xj = xb + (int64_t)j * nRHS * kTB;
+      if (!TR) {
+        T x[NR][3];
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+#pragma unroll
+          for (int u = 0; u < 3; u++)
+            x[q][u] = (q < ng) ? chainAwait<T>(xj + (int64_t)(g0 + q) * kTB + lane + 32 * u, epoch) : T(0);
+#pragma unroll
+        for (int q = 0; q < NR; q++) {
+          T sr[kChRows];
+#pragma unroll
+          for (int a = 0; a < kChRows; a++) sr[a] = t[a][0] * x[q][0] + t[a][1] * x[q][1] + t[a][2] * x[q][2];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int a = 0; a < kChRows; a++) sr[a] += __shfl_xor_sync(0xffffffffu, sr[a], o);
+#pragma unroll
+          for (int a = 0; a < kChRows; a++)
+            if (lane == a) acc[q] += sr[a];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NR; q++) {
+          // lane a < 12 fetches the value of tile row 12 w + a, then the warp shares the 12 values
+          T mine = T(0);
+          if (q < ng && lane < kChRows) mine = chainAwait<T>(xj + (int64_t)(g0 + q) * kTB + warp * kChRows + lane, epoch);
+#pragma unroll
+          for (int a = 0; a < kChRows; a++) {
+            const T xv = __shfl_sync(0xffffffffu, mine, a);
+#pragma unroll
+            for (int u = 0; u < 3; u++) pc[q][u] += t[a][u] * xv;
+          }
+        }
+      }
+    };
+    auto load = [&](T(&t)[kChRows][3], int s) {
+      const int j = TR ? nbk - 1 - s : s;
+      if (!TR)
+        chainLoadTile<T>(t, L, ldl, i0, (int64_t)j * kTB, n, warp, lane);
+      else
+        chainLoadTile<T>(t, L, ldl, (int64_t)j * kTB, i0, n, warp, lane);
+    };
+
+    {
+      T tA[kChRows][3], tB[kChRows][3];
+      if (cnt > 0) load(tA, 0);
+      for (int s = 0; s < cnt; s += 2) {
+        if (s + 1 < cnt) load(tB, s + 1);
+        consume(tA, s);
+        if (s + 1 < cnt) {
+          if (s + 2 < cnt) load(tA, s + 2);
+          consume(tB, s + 1);
+        }
+      }
+    }
+
+    // y = b_i - sum
+    if (!TR) {
+      if (lane < kChRows) {
+        const int row = warp * kChRows + lane;
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          ys[q * kTB + row] = (q < ng && row < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + row] - acc[q] : T(0);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NR; q++)
+#pragma unroll
+        for (int u = 0; u < 3; u++) part[(warp * NR + q) * kTB + lane + 32 * u] = pc[q][u];
+      __syncthreads();
+      for (int idx = tid; idx < NR * kTB; idx += kChThreads) {
+        const int q = idx / kTB, c = idx % kTB;
+        T v = T(0);
+#pragma unroll
+        for (int w = 0; w < kChWarps; w++) v += part[(w * NR + q) * kTB + c];
+        ys[idx] = (q < ng && c < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + c] - v : T(0);
+      }
+    }
+    __syncthreads();  // ys (and, first time round, Wsm) complete
+    // x_i = W y  (backward: Wsm holds W^T, so the same row-times-vector product gives W^T y)
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+      if (q < ng) {
+        const T y0 = ys[q * kTB + lane], y1 = ys[q * kTB + lane + 32], y2 = ys[q * kTB + lane + 64];
+        T sr[kChRows];
+#pragma unroll
+        for (int a = 0; a < kChRows; a++) {
+          const T* wr = Wsm + (warp * kChRows + a) * kTB;
+          sr[a] = wr[lane] * y0 + wr[lane + 32] * y1 + wr[lane + 64] * y2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int a = 0; a < kChRows; a++) sr[a] += __shfl_xor_sync(0xffffffffu, sr[a], o);
+        T xo = T(0);
+#pragma unroll
+        for (int a = 0; a < kChRows; a++)
+          if (lane == a) xo = sr[a];
+        const int row = warp * kChRows + lane;
+        if (lane < kChRows) {
+          // all 96 slots are published (rows past a partial last block carry 0: W is zero padded)
+          chainPublish(xb + ((int64_t)i * nRHS + g0 + q) * kTB + row, xo, epoch);
+          if (row < ib) C[(int64_t)(g0 + q) * ldc + i0 + row] = xo;
+        }
+      }
+    }
+    __syncthreads();  // ys / part are reused by the next group of right-hand sides
+  }
+}
+
+template <typename T>
 __global__ void copy_vec_kernel(int64_t n, int nRHS, Operand<T> Xop, int64_t ldx, Operand<T> Cop, int64_t ldc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * nRHS) return;
@@ -615,8 +903,40 @@ static void launchStepInv(cudaStream_t st, dim3 grid, bool pdl, int64_t n, int64
 }
 
 template <typename T>
+void invertBlockList(cudaStream_t st, int batch, const InvBlockDesc* list, int64_t count, Operand<T> data,
+                     Operand<T> invScratch) {
+  if (count <= 0) return;
+  const size_t ismem = ((size_t)2 * kTB * kTLD + kTB) * sizeof(T);
+  static bool once = [&] {
+    B200_CUDA(cudaFuncSetAttribute(invert_blocks_list_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+    return true;
+  }();
+  (void)once;
+  ProfScope prof(st, KC_SOLVE_DENSE, 0, (double)count * kTB * kTB / 2 * sizeof(T) * batch);
+  invert_blocks_list_kernel<T><<<dim3((unsigned)count, 1, batch), 128, ismem, st>>>(list, data, invScratch);
+  B200_LAUNCH_CHECK();
+}
+
+template <typename T, bool TR, int NR>
+static void launchChain(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc,
+                        int nRHS, Operand<T> W, ChainSync* cs) {
+  const int nbk = ceilDiv(n, kTB);
+  const size_t smem = ((size_t)kTB * kTB + (size_t)NR * kTB + (TR ? (size_t)kChWarps * NR * kTB : 0)) * sizeof(T);
+  static bool once = [&] {
+    B200_CUDA(cudaFuncSetAttribute(trsv_chain_kernel<T, TR, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return true;
+  }();
+  (void)once;
+  cs->epoch += 1;
+  trsv_chain_kernel<T, TR, NR><<<dim3((unsigned)nbk * batch, 1, 1), kChThreads, smem, st>>>(
+      n, nbk, L, ldl, C, ldc, nRHS, W, (uint4*)cs->xbuf, cs->blocksPerItem, cs->ticket, cs->ticketBase, cs->epoch);
+  B200_LAUNCH_CHECK();
+  cs->ticketBase += (unsigned)nbk * batch;
+}
+
+template <typename T>
 void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
-             bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady) {
+             bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady, ChainSync* chain) {
   if (n <= 0 || nRHS <= 0) return;
   const int nb = kTB;
   // BSPB200_PDL=0 disables the programmatic dependent launches; profiling (events between the steps) does too
@@ -646,6 +966,17 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
     ProfScope prof(st, KC_SOLVE_DENSE, 0, (double)n * kTB / 2 * sizeof(T) * batch);
     invert_blocks_kernel<T><<<dim3(ceilDiv(n, nb), 1, batch), 128, ismem, st>>>(n, L, ldl, invScratch);
     B200_LAUNCH_CHECK();
+  }
+  if (useInv && chain && chain->xbuf && ceilDiv(n, nb) <= chain->blocksPerItem && nRHS <= chain->rhsCap) {
+    ProfScope prof(st, KC_SOLVE_DENSE, (double)n * n * nRHS * batch, (double)n * (n + 1) / 2 * sizeof(T) * batch);
+    if (nRHS == 1) {
+      if (transposed) launchChain<T, true, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+      else launchChain<T, false, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+    } else {
+      if (transposed) launchChain<T, true, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+      else launchChain<T, false, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+    }
+    return;
   }
   if (!transposed) {
     for (int64_t j0 = 0; j0 < n; j0 += nb) {
@@ -680,12 +1011,13 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
 
 #define B200_INSTANTIATE_SOLVE(T)                                                                                       \
   template void gemvRows<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t,          \
-                            Operand<T>, int64_t, int64_t, int, bool);                                                   \
+                            Operand<T>, int64_t, int64_t, int, bool, const int64_t*);                                   \
   template void gemvColsT<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t, int64_t, \
-                             Operand<T>, int64_t, int);                                                                 \
+                             Operand<T>, int64_t, int, Operand<T>, int64_t, const int64_t*);                            \
   template void symmLower<T>(cudaStream_t, int, int64_t, T, Operand<T>, Operand<T>, int64_t, Operand<T>, int64_t, int); \
   template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>, \
-                           Operand<T>, bool);
+                           Operand<T>, bool, ChainSync*);                                                               \
+  template void invertBlockList<T>(cudaStream_t, int, const InvBlockDesc*, int64_t, Operand<T>, Operand<T>);
 B200_INSTANTIATE_SOLVE(double)
 B200_INSTANTIATE_SOLVE(float)
 

@@ -58,23 +58,22 @@ inline const ComputationModel* pickModel(int id) {
     case 0: return &ComputationModel::model_OpenBlas_i7_1185g7;
     case 1: return &ComputationModel::model_Cuda117_2080Ti;
     case 2: return &ComputationModel::model_B200;
-    case 3: {  // experimentation: 20 comma-separated coefficients (potrf 4, trsm 6, syge 6, asmbl 4) in BSPB200_MODEL_PARAMS
-      static ComputationModel custom = [] {
-        ComputationModel m = ComputationModel::model_B200;
-        if (const char* e = getenv("BSPB200_MODEL_PARAMS")) {
-          std::vector<double> v;
-          std::stringstream ss(e);
-          std::string tok;
-          while (std::getline(ss, tok, ',')) v.push_back(atof(tok.c_str()));
-          if (v.size() == 20) {
-            for (int i = 0; i < 4; i++) m.potrfParams[i] = v[i];
-            for (int i = 0; i < 6; i++) m.trsmParams[i] = v[4 + i];
-            for (int i = 0; i < 6; i++) m.sygeParams[i] = v[10 + i];
-            for (int i = 0; i < 4; i++) m.asmblParams[i] = v[16 + i];
-          }
+    case 3: {  // tuning hook: 20 comma-separated coefficients (potrf 4, trsm 6, syge 6, asmbl 4) in BSPB200_MODEL_PARAMS,
+               // re-read at every call so tools/model_fit.py can sweep presets inside one process
+      static thread_local ComputationModel custom;
+      custom = ComputationModel::model_B200;
+      if (const char* e = getenv("BSPB200_MODEL_PARAMS")) {
+        std::vector<double> v;
+        std::stringstream ss(e);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) v.push_back(atof(tok.c_str()));
+        if (v.size() == 20) {
+          for (int i = 0; i < 4; i++) custom.potrfParams[i] = v[i];
+          for (int i = 0; i < 6; i++) custom.trsmParams[i] = v[4 + i];
+          for (int i = 0; i < 6; i++) custom.sygeParams[i] = v[10 + i];
+          for (int i = 0; i < 4; i++) custom.asmblParams[i] = v[16 + i];
         }
-        return m;
-      }();
+      }
       return &custom;
     }
     default: return nullptr;

@@ -318,3 +318,68 @@ def test_grid_wide_and_small_lumps(model):
     xr = rhs.copy()
     o.solve(ref, xr)
     assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n_blocks3", [40, 130, 200])
+def test_chain_solve_wide_lump(dtype, n_blocks3, monkeypatch):
+    """flag-chained dense triangular solve (trsv_chain_kernel: one launch per lump and direction): a dense lump of
+    2 / 5 / 7 block rows (the last one partial), nRHS 1 (NR=1 instantiation) and 5 (two groups of the NR=4 one),
+    L / Lt / LLt separately, against the oracle, dense triangular solves, and the per-step launch path of the same
+    library (BSPB200_CHAIN_SOLVE=0)"""
+    sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_FLAT, [n_blocks3, 1.0], 3, 3, 37)
+    g, o = make_pair(sizes, ptrs, inds, find_sparse_elim_ranges=False)
+    monkeypatch.setenv("BSPB200_CHAIN_SOLVE", "0")
+    g_steps = bsp.Solver.create(sizes, ptrs, inds, (), find_sparse_elim_ranges=False,
+                                computation_model=_capi.MODEL_CUDA_2080TI)
+    monkeypatch.delenv("BSPB200_CHAIN_SOLVE")
+    assert np.diff(g.lumpStart).max() > 96
+    data = H.make_data(g, 11, dtype, 1.2)
+    d = torch_of(data)
+    g.factor(d)
+    fac = d.cpu().numpy()
+    Lm = np.tril(g.densify(fac).astype(np.float64))
+    tol = H.ORACLE_RTOL[dtype] * 50
+    for nrhs in (1, 5):
+        rhs = H.oapi().random_data_array(g.order * nrhs, -1, 1, 38 + nrhs, dtype=dtype).reshape(nrhs, g.order)
+        b = rhs.astype(np.float64).T
+        for mode in (bsp.SOLVE_L, bsp.SOLVE_LT, bsp.SOLVE_LLT):
+            for rep in range(2):  # twice: the second launch runs on advanced epochs / tickets
+                x = torch_of(rhs)
+                g.solve(d, x, mode)
+            got = x.cpu().numpy().astype(np.float64).T
+            if mode == bsp.SOLVE_L:
+                exp = np.linalg.solve(Lm, b)
+            elif mode == bsp.SOLVE_LT:
+                exp = np.linalg.solve(Lm.T, b)
+            else:
+                exp = np.linalg.solve(Lm.T, np.linalg.solve(Lm, b))
+            scale = max(1.0, np.abs(exp).max())
+            assert np.abs(got - exp).max() <= tol * scale
+            xr = rhs.copy()
+            o.solve(fac, xr, mode)
+            assert np.abs(got - xr.astype(np.float64).T).max() <= tol * scale
+            xs = torch_of(rhs)
+            g_steps.solve(d, xs, mode)
+            assert np.abs(got - xs.cpu().numpy().astype(np.float64).T).max() <= tol * scale
+
+
+def test_chain_solve_batched_wide_lump():
+    """batched solve whose dense lump spans several block rows: more chain CTAs (batch x blocks) than one wave of
+    resident CTAs is not needed for correctness - the arrival ticket orders them - checked per item"""
+    import torch
+    n_pts, n_cams, batch = 3000, 60, 37
+    sizes, ptrs, inds = H.ba_problem(n_pts, n_cams, seed=21, window=12)
+    g, o = make_pair(sizes, ptrs, inds, [0, n_pts], computation_model=_capi.MODEL_B200)
+    assert np.diff(g.lumpStart).max() >= 300
+    datas = [H.make_data(g, 500 + q, np.float64, 1.2) for q in range(batch)]
+    dev = torch.stack([torch_of(dd) for dd in datas])
+    g.factor_batched(dev)
+    rhs = [H.oapi().random_data_array(g.order, -1, 1, 900 + q).reshape(1, g.order) for q in range(batch)]
+    xs = torch.stack([torch_of(r) for r in rhs])
+    g.solve_batched(dev, xs)
+    for q in range(0, batch, 6):
+        ref, xr = datas[q].copy(), rhs[q].copy()
+        o.factor(ref)
+        o.solve(ref, xr)
+        assert np.abs(xs[q].cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
