@@ -98,23 +98,26 @@ template <typename T>
 void invertBlockList(cudaStream_t st, int batch, const InvBlockDesc* list, int64_t count, Operand<T> data,
                      Operand<T> invScratch);
 
-// state of the chained triangular solve (trsv_chain_kernel): the device exchange buffer of self-validating
-// {value, epoch} slots + the arrival ticket, and the host-side running epoch / ticket values of the launches issued so
-// far (one stream, launches in order)
+// synchronisation state of the chained triangular solve (trsv_chain_kernel): device flags + arrival ticket, and the
+// host-side running epoch / ticket values of the launches issued so far (one stream, launches in order)
 struct ChainSync {
-  void* xbuf = nullptr;        // uint4 [batch][blocksPerItem][rhsCap][96], zeroed once (epoch 0 is never used)
+  unsigned* flags = nullptr;   // [batch][flagsPerItem], zeroed once (epoch 0 is never used)
   unsigned* ticket = nullptr;  // never reset
   unsigned epoch = 0, ticketBase = 0;
-  int blocksPerItem = 0, rhsCap = 0;
+  int flagsPerItem = 0;
 };
 
 // tril(L) X = C (transposed=false) or tril(L)^T X = C (transposed=true), L n x n row-major (ldl), any n
+// returns true when the update of the rows below (rowsBelow, rowMap, vec) was done as part of the solve
 template <typename T>
-void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
+bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
              bool transposed, Operand<T> scratch /* n x nRHS per batch item, used when n > one block */,
              Operand<T> invScratch /* optional: 2 x 96 x 96 x ceil(n / 96) per batch item -> inverse-based block steps */,
              bool inversesReady = false /* the scratch already holds the inverses of this matrix */,
-             ChainSync* chain = nullptr /* with invScratch: one flag-chained launch instead of one launch per block */);
+             ChainSync* chain = nullptr /* with invScratch: one chained launch instead of one launch per block */,
+             int64_t rowsBelow = 0 /* forward + chain only: the lump's rows below the diagonal block (contiguous after */,
+             const int64_t* rowMap = nullptr /* it, same ld) update vec[rowMap[r]] -= L21[r,:] x inside the same launch */,
+             Operand<T> vec = Operand<T>() /* the whole vector (C is the lump's slice of it) */);
 
 // out[i * outRowStride + c * outColStride] (+)= alpha * sum_q M[i][q] * X[c * ldx + q]   (M rows x cols, ldm)
 // (tmp row-major rows x nRHS: strides (nRHS, 1); a column-major vector: strides (1, ld))

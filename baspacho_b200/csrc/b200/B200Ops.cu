@@ -279,23 +279,19 @@ struct B200SymbolicCtx : SymbolicCtx {
     return *belowRowsPtr;
   }
   ChainSync chain;
-  DevBuf<unsigned> chainTicket;
-  DevBuf<unsigned char> chainXbuf;
+  DevBuf<unsigned> chainBuf;
   int chainBatch = 0;
-  ChainSync* chainSync(int batch, int nRHS) {
+  ChainSync* chainSync(int batch) {
     if (!useChainSolve) return nullptr;
     const InvPlan& ip = invPlan();
     if (ip.maxBlocks == 0) return nullptr;
-    if (batch > chainBatch || nRHS > chain.rhsCap) {
+    if (batch > chainBatch) {
       B200_CUDA(cudaStreamSynchronize(stream));
-      chainBatch = std::max(batch, chainBatch), chain.rhsCap = std::max(nRHS, chain.rhsCap);
-      chainXbuf.resize((size_t)chainBatch * ip.maxBlocks * chain.rhsCap * kInvBlock * 16);
-      B200_CUDA(cudaMemset(chainXbuf.ptr(), 0, chainXbuf.size()));  // tags 0: the epoch starts at 1 and only grows
-      if (!chainTicket.ptr()) {
-        chainTicket.resize(1);
-        B200_CUDA(cudaMemset(chainTicket.ptr(), 0, sizeof(unsigned)));
-      }
-      chain.xbuf = chainXbuf.ptr(), chain.ticket = chainTicket.ptr(), chain.blocksPerItem = (int)ip.maxBlocks;
+      chainBuf.resize((size_t)ip.maxBlocks * batch + 1);
+      B200_CUDA(cudaMemset(chainBuf.ptr(), 0, chainBuf.size() * sizeof(unsigned)));
+      chain.flags = chainBuf.ptr() + 1, chain.ticket = chainBuf.ptr();
+      chain.flagsPerItem = (int)ip.maxBlocks, chain.ticketBase = 0;  // epoch keeps growing: zeroed flags never match it
+      chainBatch = batch;
     }
     return &chain;
   }
@@ -626,12 +622,19 @@ struct B200SolveCtx : SolveCtx<TT> {
     for (int64_t l = denseFrom; l < upToLump; l++) {
       const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
       const int64_t off = skel.lumpDataOffset(l);
-      solveL(data, off, n, C, start, ldc);
-      if (rows == 0) continue;
-      // C[rows below] -= L21 x_l: gemv + assembleVec of the reference sequence in one kernel (scatter through the row table)
+      // x_l = L_ll^-1 b_l, then C[rows below] -= L21 x_l (gemv + assembleVec of the reference sequence): inside the
+      // chained launch for lumps of two or more blocks, else one gemv kernel that scatters through the row table
       const auto& br = sym.belowRows();
       BASPACHO_CHECK_EQ(br.ptr[l + 1] - br.ptr[l], rows);
       Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+      bool ready = false;
+      Operand<T> inv = invScratch(off, n, &ready);
+      // BSPB200_CHAIN_FUSE_GEMV=0: rows below in a separate gemv launch (GRID solve 11.4 ms vs 10.7 ms fused)
+      static const bool fuseBelow = !(getenv("BSPB200_CHAIN_FUSE_GEMV") && atoi(getenv("BSPB200_CHAIN_FUSE_GEMV")) == 0);
+      const bool belowDone =
+          trsvAny<T>(sym.stream, m.batch, n, opnd(m, off), n, opnd(v, start), ldc, nRHS, false, opnd(temp2(), 0), inv, ready,
+                     sym.chainSync(m.batch), fuseBelow ? rows : 0, br.target.ptr() + br.ptr[l], opnd(v, 0));
+      if (rows == 0 || belowDone) continue;
       gemvRows<T>(sym.stream, m.batch, rows, n, T(-1), opnd(m, off + n * n), n, opnd(v, start), ldc, opnd(v, 0), 1, ldc, nRHS,
                   true, br.target.ptr() + br.ptr[l]);
     }
@@ -700,7 +703,7 @@ struct B200SolveCtx : SolveCtx<TT> {
     bool ready = false;
     Operand<T> inv = invScratch(offM, n, &ready);
     trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, false, opnd(temp2(), 0), inv, ready,
-               sym.chainSync(m.batch, nRHS));
+               sym.chainSync(m.batch));
   }
 
   void solveLt(const TT* data, int64_t offM, int64_t n, TT* C, int64_t offC, int64_t ldc) override {
@@ -710,7 +713,7 @@ struct B200SolveCtx : SolveCtx<TT> {
     bool ready = false;
     Operand<T> inv = invScratch(offM, n, &ready);
     trsvAny<T>(sym.stream, m.batch, n, opnd(m, offM), n, opnd(v, offC), ldc, nRHS, true, opnd(temp2(), 0), inv, ready,
-               sym.chainSync(m.batch, nRHS));
+               sym.chainSync(m.batch));
   }
 
   void gemv(const TT* data, int64_t offM, int64_t nRows, int64_t nCols, const TT* A, int64_t offA, int64_t lda,

@@ -692,53 +692,48 @@ __global__ void __launch_bounds__(128) invert_blocks_list_kernel(const InvBlockD
 // CTA i owns block row i (forward) / block column i (backward) of the triangle. It streams its off-diagonal 96 x 96
 // tiles in the order their solved blocks become available (register double buffer: the next tile is in flight while
 // the CTA waits), accumulates tile * x_j, and as soon as the last neighbour is published finishes
-// x_i = W_i (b_i - sum) with the precomputed block inverse (staged in shared memory at kernel start) and publishes it.
-// Publication is self-validating (the scheme of NCCL's LL protocol): every solved value is stored as two 8-byte words
-// {low half, tag} {high half, tag} with tag = the launch's epoch; 8-byte accesses are single-copy atomic, so a consumer
-// that reads both tags equal to the epoch holds the value - one L2 round trip from the producer's store to the
-// consumer's registers, no flag, no fence. Consumers poll with volatile loads (L2; L1 is never involved).
-// The critical path per block is that round trip + one tile product + one 96 x 96 matvec instead of a kernel boundary.
+// x_i = W_i (b_i - sum) with the precomputed block inverse (staged in shared memory at kernel start) and publishes it:
+// store x_i, fence, release-store of the epoch into flag[i]. Consumers acquire-poll the flag and read x_i with ld.cg
+// (L1 may hold the pre-solve values of the same addresses from a CTA that ran earlier on the SM).
+// The critical path per block is flag round trip + one tile product + one 96 x 96 matvec instead of a kernel boundary.
 // CTAs take their block from an arrival ticket, so a CTA only ever waits for CTAs that arrived before it (no deadlock
-// when the grid exceeds the resident capacity, e.g. batched solves). The exchange buffer is never reset: every launch
-// uses a fresh epoch, and every right-hand side has its own slots.
+// when the grid exceeds the resident capacity, e.g. batched solves). Flags are never reset: every launch (and every
+// group of NR right-hand sides inside it) uses a fresh epoch value.
+// Measured alternatives (B200, BAL-shaped 5226-wide lump, 55 blocks per direction): this flag protocol 3.4 us per block;
+// self-validating {value, epoch} slots polled by every lane (NCCL-LL style, no fence) 4.3 us - twelve polled sectors per
+// warp instead of one; the same with __nanosleep back-off for the CTAs that are not next in the chain 9.8 us (the sleep
+// granularity makes the far CTAs fall behind and become the critical path). See profiles/README.md.
 constexpr int kChThreads = 256, kChWarps = 8, kChRows = kTB / kChWarps;  // 12 tile rows per warp
 
-__device__ __forceinline__ void chainPublish(uint4* slot, double v, unsigned tag) {
-  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
-               : "memory");
+__device__ __forceinline__ unsigned ldAcquireU32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ void chainPublish(uint4* slot, float v, unsigned tag) {
-  chainPublish(slot, (double)v, tag);
-}
-template <typename T>
-__device__ __forceinline__ T chainAwait(const uint4* slot, unsigned tag) {
-  unsigned lo, t0, hi, t1;
-  do {
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
-                 : "l"(slot)
-                 : "memory");
-  } while (t0 != tag || t1 != tag);
-  return (T)__hiloint2double((int)hi, (int)lo);
+__device__ __forceinline__ void stReleaseU32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <typename T>
 __device__ __forceinline__ void chainLoadTile(T (&t)[kChRows][3], const T* __restrict__ L, int64_t ldl, int64_t r0,
-                                              int64_t c0, int64_t n, int warp, int lane) {
+                                              int64_t c0, int64_t rowEnd, int64_t colEnd, int warp, int lane) {
 #pragma unroll
   for (int a = 0; a < kChRows; a++) {
     const int64_t row = r0 + warp * kChRows + a;
 #pragma unroll
-    for (int u = 0; u < 3; u++) t[a][u] = (row < n) ? L[row * ldl + c0 + lane + 32 * u] : T(0);
+    for (int u = 0; u < 3; u++)
+      t[a][u] = (row < rowEnd && c0 + lane + 32 * u < colEnd) ? L[row * ldl + c0 + lane + 32 * u] : T(0);
   }
 }
 
 template <typename T, bool TR, int NR>
 __global__ void __launch_bounds__(kChThreads, 1)
     trsv_chain_kernel(int64_t n, int nbk, Operand<T> Lop, int64_t ldl, Operand<T> Cop, int64_t ldc, int nRHS,
-                      Operand<T> Wop, uint4* xbuf, int blocksPerItem, unsigned* ticket, unsigned ticketBase,
-                      unsigned epoch) {
+                      Operand<T> Wop, unsigned* flags, int flagsPerItem, unsigned* ticket, unsigned ticketBase,
+                      unsigned epoch0, int64_t rowsBelow, const int64_t* __restrict__ rowMap, Operand<T> Vop) {
+  // forward only, rowsBelow > 0: the lump's rows below the diagonal block (L21, contiguous after it, same ld) ride
+  // along - extra CTAs of 96 rows each consume the solved blocks as they are published and finish the
+  // C[rowMap[r]] -= L21[r, :] x update (the gemv + assembleVec of the reference sequence) right behind the chain
   extern __shared__ __align__(16) unsigned char smemRaw[];
   T* Wsm = reinterpret_cast<T*>(smemRaw);  // [kTB][kTB] block inverse (transposed copy for the backward solve)
   T* ys = Wsm + kTB * kTB;                 // [NR][kTB]  b_i - sum
@@ -748,35 +743,67 @@ __global__ void __launch_bounds__(kChThreads, 1)
   if (tid == 0) slotS = atomicAdd(ticket, 1u) - ticketBase;
   __syncthreads();
   const unsigned slot = slotS;
-  const int item = (int)(slot / (unsigned)nbk), ord = (int)(slot % (unsigned)nbk);
+  const int perItem = nbk + (TR ? 0 : (int)((rowsBelow + kTB - 1) / kTB));
+  const int item = (int)(slot / (unsigned)perItem), ord = (int)(slot % (unsigned)perItem);
+  const bool below = !TR && ord >= nbk;
   const int i = TR ? nbk - 1 - ord : ord;
   const T* __restrict__ L = Lop.at(item);
   T* C = Cop.at(item);
   const T* __restrict__ Wm = Wop.at(item) + (int64_t)i * (2 * kTB * kTB) + (TR ? kTB * kTB : 0);
-  // exchange slots of (item, block j, right-hand side c): xb + (j * nRHS + c) * kTB
-  uint4* xb = xbuf + (int64_t)item * blocksPerItem * nRHS * kTB;
+  unsigned* flg = flags + (int64_t)item * flagsPerItem;
   const int64_t i0 = (int64_t)i * kTB;
   const int ib = (int)min((int64_t)kTB, n - i0);
-  const int cnt = ord;  // off-diagonal tiles of this CTA; the s-th one belongs to block (TR ? nbk - 1 - s : s)
-  for (int idx = tid; idx < kTB * kTB; idx += kChThreads) Wsm[idx] = Wm[idx];
+  // off-diagonal tiles of this CTA; the s-th one belongs to block (TR ? nbk - 1 - s : s)
+  const int cnt = below ? nbk : ord;
+  const int64_t rowOrg = below ? n + (int64_t)(ord - nbk) * kTB : i0;  // forward: first tile row of this CTA
+  const int64_t rowEnd = below ? n + rowsBelow : n;
+  if (!below)
+    for (int idx = tid; idx < kTB * kTB; idx += kChThreads) Wsm[idx] = Wm[idx];
 
-  for (int g0 = 0; g0 < nRHS; g0 += NR) {
+  int grp = 0;
+  for (int g0 = 0; g0 < nRHS; g0 += NR, grp++) {
+    const unsigned epoch = epoch0 + (unsigned)grp;
     const int ng = min(NR, nRHS - g0);
     T acc[NR];     // forward: lane a < 12 of warp w holds the sum of row 12 w + a
     T pc[NR][3];   // backward: partial sums of columns lane + 32 u over the warp's rows
 #pragma unroll
     for (int q = 0; q < NR; q++) acc[q] = pc[q][0] = pc[q][1] = pc[q][2] = T(0);
+    // this block's right-hand sides, requested now: off the critical path between the last neighbour and x_i
+    T bpre[TR ? (NR * kTB + kChThreads - 1) / kChThreads : NR];
+    int64_t belowDst = -1;  // below CTA: vector row this lane's tile row updates
+    if (!TR) {
+      const int row = warp * kChRows + lane;
+      if (below) {
+        if (lane < kChRows && rowOrg + row < rowEnd) belowDst = rowMap[rowOrg + row - n];
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          bpre[q] = (belowDst >= 0 && q < ng) ? Vop.at(item)[(int64_t)(g0 + q) * ldc + belowDst] : T(0);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          bpre[q] = (lane < kChRows && q < ng && row < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + row] : T(0);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < (NR * kTB + kChThreads - 1) / kChThreads; e++) {
+        const int idx = tid + e * kChThreads, q = idx / kTB, c = idx % kTB;
+        bpre[e] = (idx < NR * kTB && q < ng && c < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + c] : T(0);
+      }
+    }
 
     auto consume = [&](const T(&t)[kChRows][3], int s) {
       const int j = TR ? nbk - 1 - s : s;
-      const uint4* xj = xb + (int64_t)j * nRHS * kTB;
+      const int64_t j0 = (int64_t)j * kTB;
+      // ">= epoch" in wrap-around arithmetic: with several right-hand-side groups the producer may already be groups ahead
+      while ((int)(ldAcquireU32(flg + j) - epoch) < 0) {
+      }
       if (!TR) {
         T x[NR][3];
 #pragma unroll
         for (int q = 0; q < NR; q++)
 #pragma unroll
           for (int u = 0; u < 3; u++)
-            x[q][u] = (q < ng) ? chainAwait<T>(xj + (int64_t)(g0 + q) * kTB + lane + 32 * u, epoch) : T(0);
+            x[q][u] = (q < ng && j0 + lane + 32 * u < n) ? __ldcg(&C[(int64_t)(g0 + q) * ldc + j0 + lane + 32 * u]) : T(0);
 #pragma unroll
         for (int q = 0; q < NR; q++) {
           T sr[kChRows];
@@ -793,24 +820,25 @@ __global__ void __launch_bounds__(kChThreads, 1)
       } else {
 #pragma unroll
         for (int q = 0; q < NR; q++) {
-          // lane a < 12 fetches the value of tile row 12 w + a, then the warp shares the 12 values
-          T mine = T(0);
-          if (q < ng && lane < kChRows) mine = chainAwait<T>(xj + (int64_t)(g0 + q) * kTB + warp * kChRows + lane, epoch);
+          T xv[kChRows];
 #pragma unroll
           for (int a = 0; a < kChRows; a++) {
-            const T xv = __shfl_sync(0xffffffffu, mine, a);
-#pragma unroll
-            for (int u = 0; u < 3; u++) pc[q][u] += t[a][u] * xv;
+            const int64_t row = j0 + warp * kChRows + a;
+            xv[a] = (q < ng && row < n) ? __ldcg(&C[(int64_t)(g0 + q) * ldc + row]) : T(0);
           }
+#pragma unroll
+          for (int a = 0; a < kChRows; a++)
+#pragma unroll
+            for (int u = 0; u < 3; u++) pc[q][u] += t[a][u] * xv[a];
         }
       }
     };
     auto load = [&](T(&t)[kChRows][3], int s) {
       const int j = TR ? nbk - 1 - s : s;
       if (!TR)
-        chainLoadTile<T>(t, L, ldl, i0, (int64_t)j * kTB, n, warp, lane);
+        chainLoadTile<T>(t, L, ldl, rowOrg, (int64_t)j * kTB, rowEnd, n, warp, lane);
       else
-        chainLoadTile<T>(t, L, ldl, (int64_t)j * kTB, i0, n, warp, lane);
+        chainLoadTile<T>(t, L, ldl, (int64_t)j * kTB, i0, n, n, warp, lane);
     };
 
     {
@@ -826,13 +854,21 @@ __global__ void __launch_bounds__(kChThreads, 1)
       }
     }
 
+    if (below) {  // uniform per CTA: no block to solve, only the update of the rows below
+      if (belowDst >= 0) {
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          if (q < ng) Vop.at(item)[(int64_t)(g0 + q) * ldc + belowDst] = bpre[q] - acc[q];
+      }
+      continue;
+    }
     // y = b_i - sum
     if (!TR) {
       if (lane < kChRows) {
         const int row = warp * kChRows + lane;
 #pragma unroll
         for (int q = 0; q < NR; q++)
-          ys[q * kTB + row] = (q < ng && row < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + row] - acc[q] : T(0);
+          ys[q * kTB + row] = (q < ng && row < ib) ? bpre[q] - acc[q] : T(0);
       }
     } else {
 #pragma unroll
@@ -840,12 +876,15 @@ __global__ void __launch_bounds__(kChThreads, 1)
 #pragma unroll
         for (int u = 0; u < 3; u++) part[(warp * NR + q) * kTB + lane + 32 * u] = pc[q][u];
       __syncthreads();
-      for (int idx = tid; idx < NR * kTB; idx += kChThreads) {
-        const int q = idx / kTB, c = idx % kTB;
-        T v = T(0);
 #pragma unroll
-        for (int w = 0; w < kChWarps; w++) v += part[(w * NR + q) * kTB + c];
-        ys[idx] = (q < ng && c < ib) ? C[(int64_t)(g0 + q) * ldc + i0 + c] - v : T(0);
+      for (int e = 0; e < (NR * kTB + kChThreads - 1) / kChThreads; e++) {
+        const int idx = tid + e * kChThreads, q = idx / kTB, c = idx % kTB;
+        if (idx < NR * kTB) {
+          T v = T(0);
+#pragma unroll
+          for (int w = 0; w < kChWarps; w++) v += part[(w * NR + q) * kTB + c];
+          ys[idx] = (q < ng && c < ib) ? bpre[e] - v : T(0);
+        }
       }
     }
     __syncthreads();  // ys (and, first time round, Wsm) complete
@@ -869,14 +908,12 @@ __global__ void __launch_bounds__(kChThreads, 1)
         for (int a = 0; a < kChRows; a++)
           if (lane == a) xo = sr[a];
         const int row = warp * kChRows + lane;
-        if (lane < kChRows) {
-          // all 96 slots are published (rows past a partial last block carry 0: W is zero padded)
-          chainPublish(xb + ((int64_t)i * nRHS + g0 + q) * kTB + row, xo, epoch);
-          if (row < ib) C[(int64_t)(g0 + q) * ldc + i0 + row] = xo;
-        }
+        if (lane < kChRows && row < ib) C[(int64_t)(g0 + q) * ldc + i0 + row] = xo;
       }
     }
-    __syncthreads();  // ys / part are reused by the next group of right-hand sides
+    __threadfence();
+    __syncthreads();  // (also: ys / part are reused by the next group of right-hand sides)
+    if (tid == 0) stReleaseU32(flg + i, epoch);
   }
 }
 
@@ -919,32 +956,36 @@ void invertBlockList(cudaStream_t st, int batch, const InvBlockDesc* list, int64
 
 template <typename T, bool TR, int NR>
 static void launchChain(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc,
-                        int nRHS, Operand<T> W, ChainSync* cs) {
+                        int nRHS, Operand<T> W, ChainSync* cs, int64_t rowsBelow, const int64_t* rowMap,
+                        Operand<T> vec) {
   const int nbk = ceilDiv(n, kTB);
+  const int perItem = nbk + (TR ? 0 : ceilDiv(rowsBelow, kTB));
   const size_t smem = ((size_t)kTB * kTB + (size_t)NR * kTB + (TR ? (size_t)kChWarps * NR * kTB : 0)) * sizeof(T);
   static bool once = [&] {
     B200_CUDA(cudaFuncSetAttribute(trsv_chain_kernel<T, TR, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return true;
   }();
   (void)once;
-  cs->epoch += 1;
-  trsv_chain_kernel<T, TR, NR><<<dim3((unsigned)nbk * batch, 1, 1), kChThreads, smem, st>>>(
-      n, nbk, L, ldl, C, ldc, nRHS, W, (uint4*)cs->xbuf, cs->blocksPerItem, cs->ticket, cs->ticketBase, cs->epoch);
+  trsv_chain_kernel<T, TR, NR><<<dim3((unsigned)perItem * batch, 1, 1), kChThreads, smem, st>>>(
+      n, nbk, L, ldl, C, ldc, nRHS, W, cs->flags, cs->flagsPerItem, cs->ticket, cs->ticketBase, cs->epoch + 1,
+      TR ? 0 : rowsBelow, rowMap, vec);
   B200_LAUNCH_CHECK();
-  cs->ticketBase += (unsigned)nbk * batch;
+  cs->ticketBase += (unsigned)perItem * batch;
+  cs->epoch += (unsigned)ceilDiv(nRHS, NR);
 }
 
 template <typename T>
-void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
-             bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady, ChainSync* chain) {
-  if (n <= 0 || nRHS <= 0) return;
+bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, Operand<T> C, int64_t ldc, int nRHS,
+             bool transposed, Operand<T> scratch, Operand<T> invScratch, bool inversesReady, ChainSync* chain,
+             int64_t rowsBelow, const int64_t* rowMap, Operand<T> vec) {
+  if (n <= 0 || nRHS <= 0) return false;
   const int nb = kTB;
   // BSPB200_PDL=0 disables the programmatic dependent launches; profiling (events between the steps) does too
   static const bool pdlEnv = !(getenv("BSPB200_PDL") && atoi(getenv("BSPB200_PDL")) == 0);
   const bool pdl = pdlEnv && !profileEnabled();
   if (n <= nb) {  // a single block: solved in place
     trsvBlock<T>(st, batch, (int)n, L, ldl, C, ldc, nRHS, transposed);
-    return;
+    return false;
   }
   const size_t smem = ((size_t)kTB * kTLD + kTB + (size_t)kTrsvWarps * kTB) * sizeof(T);
   static bool once = [&] {
@@ -967,16 +1008,20 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
     invert_blocks_kernel<T><<<dim3(ceilDiv(n, nb), 1, batch), 128, ismem, st>>>(n, L, ldl, invScratch);
     B200_LAUNCH_CHECK();
   }
-  if (useInv && chain && chain->xbuf && ceilDiv(n, nb) <= chain->blocksPerItem && nRHS <= chain->rhsCap) {
-    ProfScope prof(st, KC_SOLVE_DENSE, (double)n * n * nRHS * batch, (double)n * (n + 1) / 2 * sizeof(T) * batch);
+  if (useInv && chain && chain->flags && ceilDiv(n, nb) <= chain->flagsPerItem) {
+    // the rows below ride along in the forward chain when the caller passed their row table
+    const bool fuseBelow = !transposed && rowMap != nullptr && rowsBelow > 0;
+    const int64_t rb = fuseBelow ? rowsBelow : 0;
+    ProfScope prof(st, KC_SOLVE_DENSE, ((double)n * n + 2.0 * rb * n) * nRHS * batch,
+                   ((double)n * (n + 1) / 2 + (double)rb * n) * sizeof(T) * batch);
     if (nRHS == 1) {
-      if (transposed) launchChain<T, true, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
-      else launchChain<T, false, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+      if (transposed) launchChain<T, true, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain, 0, nullptr, vec);
+      else launchChain<T, false, 1>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain, rb, rowMap, vec);
     } else {
-      if (transposed) launchChain<T, true, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
-      else launchChain<T, false, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain);
+      if (transposed) launchChain<T, true, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain, 0, nullptr, vec);
+      else launchChain<T, false, 4>(st, batch, n, L, ldl, C, ldc, nRHS, invScratch, chain, rb, rowMap, vec);
     }
-    return;
+    return fuseBelow;
   }
   if (!transposed) {
     for (int64_t j0 = 0; j0 < n; j0 += nb) {
@@ -1007,6 +1052,7 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   }
   copy_vec_kernel<T><<<dim3(ceilDiv(n * nRHS, 256), 1, batch), 256, 0, st>>>(n, nRHS, scratch, ldx, C, ldc);
   B200_LAUNCH_CHECK();
+  return false;
 }
 
 #define B200_INSTANTIATE_SOLVE(T)                                                                                       \
@@ -1015,8 +1061,8 @@ void trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   template void gemvColsT<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t, int64_t, \
                              Operand<T>, int64_t, int, Operand<T>, int64_t, const int64_t*);                            \
   template void symmLower<T>(cudaStream_t, int, int64_t, T, Operand<T>, Operand<T>, int64_t, Operand<T>, int64_t, int); \
-  template void trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>, \
-                           Operand<T>, bool, ChainSync*);                                                               \
+  template bool trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>, \
+                           Operand<T>, bool, ChainSync*, int64_t, const int64_t*, Operand<T>);                          \
   template void invertBlockList<T>(cudaStream_t, int, const InvBlockDesc*, int64_t, Operand<T>, Operand<T>);
 B200_INSTANTIATE_SOLVE(double)
 B200_INSTANTIATE_SOLVE(float)
