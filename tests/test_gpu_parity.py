@@ -383,3 +383,33 @@ def test_chain_solve_batched_wide_lump():
         o.factor(ref)
         o.solve(ref, xr)
         assert np.abs(xs[q].cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+
+
+def test_ref_cuda_baseline_against_oracle():
+    """the restated reference CUDA backend (oracle/RefCudaOps.cu: cuSOLVER/cuBLAS per lump + thread-per-pair elimination
+    with atomics) - the second GPU baseline bench.py --impl ref_cuda times - computes the same factor and solution as the
+    CPU oracle (atomics reorder the sums: tolerance, not bits)"""
+    from oracle import refcuda
+    cases = []
+    for i in range(2):
+        sizes, ptrs, inds = H.random_problem(i)
+        cases.append((sizes, ptrs, inds, ()))
+    sizes, ptrs, inds = H.ba_problem(300, 12, seed=61, window=4)
+    cases.append((sizes, ptrs, inds, (0, 300)))
+    for ci, (sizes, ptrs, inds, ranges) in enumerate(cases):
+        kw = dict(computation_model=_capi.MODEL_CUDA_2080TI)
+        r = refcuda.RefCudaSolver.create(sizes, ptrs, inds, list(ranges), **kw)
+        o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, list(ranges), backend=_capi.BACKEND_REF, **kw)
+        for name in _capi.ARRAY_IDS:
+            np.testing.assert_array_equal(r.array(name), o.array(name), err_msg=name)
+        data = H.make_data(r, 21 + ci, np.float64)
+        rhs = H.oapi().random_data_array(r.order * 2, -1, 1, 70 + ci).reshape(2, r.order)
+        d, x = torch_of(data), torch_of(rhs)
+        r.factor(d)
+        r.solve(d, x)
+        ref, xr = data.copy(), rhs.copy()
+        o.factor(ref)
+        o.solve(ref, xr)
+        mask = np.tril(r.densify(np.ones_like(data))) > 0
+        assert np.abs(r.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+        assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())

@@ -87,3 +87,13 @@ def test_product_library_has_no_cpu_numeric_path():
     for backend in (_capi.BACKEND_REF, _capi.BACKEND_FAST):
         with pytest.raises(_capi.BaspachoError):
             bsp.Solver.create(sizes, ptrs, inds, backend=backend)
+
+
+def test_ref_cuda_baseline_library_loads():
+    """oracle/liboracle_refcuda.so (second GPU baseline, measurement infrastructure) builds, loads and exports the C ABI;
+    it needs a device to create a solver (cuBLAS handle) - no compute here"""
+    from oracle import refcuda
+    a = refcuda.api()
+    assert b"ref-cuda" in a.version()
+    for sym in ("create_solver", "factor", "solve", "set_stream", "do_elimination"):
+        assert hasattr(a.lib, "refcuda_" + sym)
