@@ -101,3 +101,18 @@ def test_amd_fill_quality_bound():
     sizes, gp, gi = H.oapi().gen_pattern_arrays(H.GEN_GRID, [14, 14, 1.0, 1], 1, 1, 37)
     perm = H.oapi().amd(gp, gi)
     assert _fill_count(len(sizes), gp, gi, perm) < 0.85 * _fill_count(len(sizes), gp, gi, np.arange(len(sizes)))
+
+
+def test_cost_model_fit_tool_on_committed_timings():
+    """tools/model_fit.py: the weighted least-squares fit of the reference's functional forms runs on the
+    committed B200 timings and reproduces potrf / syge within the stated errors"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(__file__), "..")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "model_fit.py"), "fit", "--data",
+                          os.path.join(root, "profiles", "r01_model_fit_collect.json")], capture_output=True, text=True, check=True).stdout
+    summary = json.loads(out[:out.index("\nsweep")])
+    assert len(summary["fitted_params"]) == 20
+    assert summary["median_rel_err"]["potrf"] < 0.1 and summary["median_rel_err"]["syge"] < 0.15
