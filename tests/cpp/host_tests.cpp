@@ -27,6 +27,9 @@
 #include "../../baspacho_b200/csrc/host/SparseStructure.h"
 #include "../../baspacho_b200/csrc/host/Utils.h"
 #include "../../baspacho_b200/csrc/testing/TestingUtils.h"
+#include "../../oracle/BlasLoader.h"
+#include <functional>
+#include <memory>
 
 using namespace BaSpaCho;
 using namespace BaSpaCho::testing_utils;
@@ -339,6 +342,179 @@ static void testCreateSolver(bool elimSet, bool lastIds, int reps, double eps) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- partial factor / solve
+// PartialFactorSolveTest.cpp:48-560: a skeleton with a sparse-elimination range and a merge barrier at span `nocross`;
+// every partial entry point of Solver against dense algebra on the densified matrix, for a CPU checker backend.
+struct PartialCase {
+  std::unique_ptr<Solver> solver;
+  int64_t nocross, order, barrierAt;
+};
+static PartialCase makePartialCase(int i, const std::function<OpsPtr()>& genOps) {
+  const int64_t kMinElim = 50;
+  ColumnSets colBlocks = randomCols(215, 0.03, 57 + i);
+  colBlocks = makeIndependentElimSet(colBlocks, 0, 150);
+  SparseStructure sortedSs = columnsToCscStruct(colBlocks).transpose();
+  PartialCase pc;
+  pc.nocross = (7 * i) % (210 - kMinElim) + kMinElim + 1;
+  vector<int64_t> paramSize = randomVec(sortedSs.order(), 2, 3, 47);
+  EliminationTree et(paramSize, sortedSs);
+  et.buildTree();
+  et.processTree(/*detectSparseElimRanges=*/true, {pc.nocross});
+  et.computeAggregateStruct();
+  CoalescedBlockMatrixSkel skel(et.computeSpanStart(), et.lumpToSpan, et.colStart, et.rowParam);
+  if (skel.spanOffsetInLump[pc.nocross] != 0 || et.sparseElimRanges.size() < 2) return pc;  // solver stays null -> CHECK fails
+  pc.order = skel.order();
+  pc.barrierAt = skel.spanStart[pc.nocross];
+  vector<int64_t> ranges = et.sparseElimRanges;
+  pc.solver.reset(new Solver(std::move(skel), std::move(ranges), {}, genOps()));
+  return pc;
+}
+static double relLowerDiff(const vector<double>& a, const vector<double>& b, int64_t n) {
+  double num = 0, den = 0;
+  for (int64_t r = 0; r < n; r++)
+    for (int64_t c = 0; c <= r; c++) num += (a[r * n + c] - b[r * n + c]) * (a[r * n + c] - b[r * n + c]), den += a[r * n + c] * a[r * n + c];
+  return std::sqrt(num / den);
+}
+static double relDiff(const vector<double>& a, const vector<double>& b) {
+  double num = 0, den = 0;
+  for (size_t i = 0; i < a.size(); i++) num += (a[i] - b[i]) * (a[i] - b[i]), den += a[i] * a[i];
+  return std::sqrt(num / den);
+}
+
+template <typename T>
+static void testPartial(const std::function<OpsPtr()>& genOps, int reps, double eps) {
+  for (int i = 0; i < reps; i++) {
+    // ---- PartialFactor / SplitFactor / testPseudoFactor (matrix strongly damped)
+    {
+      PartialCase pc = makePartialCase(i, genOps);
+      CHECK(pc.solver != nullptr);
+      const int64_t n = pc.order;
+      vector<T> data = randomData<T>(pc.solver->dataSize(), T(-1), T(1), 9 + i);
+      pc.solver->skel().damp(data, T(0), T(n * 2.0));
+      vector<T> d0 = pc.solver->skel().densify(data);
+      vector<double> lower(d0.begin(), d0.end());
+      for (int64_t r = 0; r < n; r++)
+        for (int64_t c = r + 1; c < n; c++) lower[r * n + c] = 0;
+
+      vector<double> marginal = lower, full = lower;
+      denseCholeskyLeading(marginal, n, pc.barrierAt);
+      denseCholeskyLeading(full, n, n);
+      vector<T> part = data;
+      pc.solver->factorUpTo(part.data(), pc.nocross);
+      vector<T> gotPart = pc.solver->skel().densify(part);
+      CHECK(relLowerDiff(marginal, vector<double>(gotPart.begin(), gotPart.end()), n) < eps);
+      pc.solver->factorFrom(part.data(), pc.nocross);
+      vector<T> gotFull = pc.solver->skel().densify(part);
+      CHECK(relLowerDiff(full, vector<double>(gotFull.begin(), gotFull.end()), n) < eps);
+
+      // pseudo factor: per span, Cholesky of the span's diagonal block and the rows below solved against it
+      vector<double> pseudo = lower;
+      const auto& sk = pc.solver->skel();
+      for (int64_t j = 0; j < sk.numSpans(); j++) {
+        const int64_t b = sk.spanStart[j], e = sk.spanStart[j + 1];
+        for (int64_t c = b; c < e; c++) {  // in-block Cholesky, then rows below: x L^T = row
+          double d = pseudo[c * n + c];
+          for (int64_t q = b; q < c; q++) d -= pseudo[c * n + q] * pseudo[c * n + q];
+          d = std::sqrt(d);
+          pseudo[c * n + c] = d;
+          for (int64_t r = c + 1; r < n; r++) {
+            double v = pseudo[r * n + c];
+            for (int64_t q = b; q < c; q++) v -= pseudo[r * n + q] * pseudo[c * n + q];
+            pseudo[r * n + c] = v / d;
+          }
+        }
+      }
+      vector<T> ps = data;
+      pc.solver->pseudoFactorFrom(ps.data(), 0);
+      vector<T> gotPs = sk.densify(ps);
+      CHECK(relLowerDiff(pseudo, vector<double>(gotPs.begin(), gotPs.end()), n) < eps);
+
+      // addMvFrom: out[after] += sym(A[after, after]) in[after]
+      const int nRHS = 3;
+      vector<T> vin = randomData<T>(n * nRHS, T(-1), T(1), 49 + i), vout = vin;
+      vector<double> ref(vout.begin(), vout.end());
+      for (int c = 0; c < nRHS; c++)
+        for (int64_t r = pc.barrierAt; r < n; r++) {
+          double acc = 0;
+          for (int64_t q = pc.barrierAt; q < n; q++) acc += (q <= r ? lower[r * n + q] : lower[q * n + r]) * vin[c * n + q];
+          ref[c * n + r] += acc;
+        }
+      pc.solver->addMvFrom(data.data(), pc.nocross, vin.data(), n, vout.data(), n, nRHS);
+      CHECK(relDiff(ref, vector<double>(vout.begin(), vout.end())) < eps);
+    }
+    // ---- PartialSolveL / Lt (UpTo) and (From): the data is used AS the factor (mildly damped, as the reference does)
+    {
+      PartialCase pc = makePartialCase(i, genOps);
+      CHECK(pc.solver != nullptr);
+      const int64_t n = pc.order, bar = pc.barrierAt;
+      vector<T> data = randomData<T>(pc.solver->dataSize(), T(-1), T(1), 9 + i);
+      pc.solver->skel().damp(data, T(0), T(3.0));
+      vector<T> d0 = pc.solver->skel().densify(data);
+      vector<double> L(d0.begin(), d0.end());
+      const int nRHS = 3;
+      for (int j = 0; j < 2; j++) {
+        vector<T> v0 = randomData<T>(n * nRHS, T(-1), T(1), 49 + j + i);
+        vector<double> b(v0.begin(), v0.end());
+        // solveLUpTo: top = L11^-1 top ; bottom -= L21 top
+        vector<double> ref = b;
+        for (int c = 0; c < nRHS; c++) {
+          double* x = ref.data() + c * n;
+          for (int64_t r = 0; r < bar; r++) {
+            double s = x[r];
+            for (int64_t q = 0; q < r; q++) s -= L[r * n + q] * x[q];
+            x[r] = s / L[r * n + r];
+          }
+          for (int64_t r = bar; r < n; r++)
+            for (int64_t q = 0; q < bar; q++) x[r] -= L[r * n + q] * x[q];
+        }
+        vector<T> v = v0;
+        pc.solver->solveLUpTo(data.data(), pc.nocross, v.data(), n, nRHS);
+        CHECK(relDiff(ref, vector<double>(v.begin(), v.end())) < eps);
+        // solveLtUpTo: top -= L21^T bottom ; top = L11^-T top
+        ref = b;
+        for (int c = 0; c < nRHS; c++) {
+          double* x = ref.data() + c * n;
+          for (int64_t q = 0; q < bar; q++)
+            for (int64_t r = bar; r < n; r++) x[q] -= L[r * n + q] * x[r];
+          for (int64_t r = bar - 1; r >= 0; r--) {
+            double s = x[r];
+            for (int64_t q = r + 1; q < bar; q++) s -= L[q * n + r] * x[q];
+            x[r] = s / L[r * n + r];
+          }
+        }
+        v = v0;
+        pc.solver->solveLtUpTo(data.data(), pc.nocross, v.data(), n, nRHS);
+        CHECK(relDiff(ref, vector<double>(v.begin(), v.end())) < eps);
+        // solveLFrom / solveLtFrom: only the trailing block
+        ref = b;
+        for (int c = 0; c < nRHS; c++) {
+          double* x = ref.data() + c * n;
+          for (int64_t r = bar; r < n; r++) {
+            double s = x[r];
+            for (int64_t q = bar; q < r; q++) s -= L[r * n + q] * x[q];
+            x[r] = s / L[r * n + r];
+          }
+        }
+        v = v0;
+        pc.solver->solveLFrom(data.data(), pc.nocross, v.data(), n, nRHS);
+        CHECK(relDiff(ref, vector<double>(v.begin(), v.end())) < eps);
+        ref = b;
+        for (int c = 0; c < nRHS; c++) {
+          double* x = ref.data() + c * n;
+          for (int64_t r = n - 1; r >= bar; r--) {
+            double s = x[r];
+            for (int64_t q = r + 1; q < n; q++) s -= L[q * n + r] * x[q];
+            x[r] = s / L[r * n + r];
+          }
+        }
+        v = v0;
+        pc.solver->solveLtFrom(data.data(), pc.nocross, v.data(), n, nRHS);
+        CHECK(relDiff(ref, vector<double>(v.begin(), v.end())) < eps);
+      }
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   registerBackend(BackendRef, [](int) { return oracleRefOps(); });
   registerBackend(BackendFast, [](int n) { return oracleFastOps(n); });
@@ -361,7 +537,26 @@ int main(int argc, char** argv) {
       {"CreateSolver.Elim_float", [&] { testCreateSolver<float>(true, false, reps, 2e-5); }},
       {"CreateSolver.Last_double", [&] { testCreateSolver<double>(false, true, reps, 1e-9); }},
       {"CreateSolver.ElimLast_double", [&] { testCreateSolver<double>(true, true, reps, 1e-9); }},
+      {"Partial.{PartialFactor,SplitFactor,PseudoFactor,PartialAddMv,PartialSolveL/Lt(+From)}_Ref_double",
+       [&] { testPartial<double>([] { return oracleRefOps(); }, reps, 1e-9); }},
+      {"Partial.*_Ref_float", [&] { testPartial<float>([] { return oracleRefOps(); }, reps, 5e-5); }},
   };
+  // BackendFast needs a BLAS: tests/test_host_cpp.py passes the OpenBLAS the python side found
+  if (const char* blas = getenv("ORACLE_BLAS_PATH")) {
+    std::string err;
+    const char* prefix = getenv("ORACLE_BLAS_PREFIX");
+    if (oracle_blas::load(blas, prefix ? prefix : "", "", &err)) {
+      cases.push_back({"Partial.*_Blas_double", [&] { testPartial<double>([] { return oracleFastOps(4); }, reps, 1e-9); }});
+      cases.push_back({"Partial.*_Blas_float", [&] { testPartial<float>([] { return oracleFastOps(4); }, reps, 5e-5); }});
+      cases.push_back({"CreateSolver.Plain_Blas_double", [&] {
+                         registerBackend(BackendRef, [](int) { return oracleFastOps(4); });
+                         testCreateSolver<double>(false, false, reps, 1e-9);
+                         registerBackend(BackendRef, [](int) { return oracleRefOps(); });
+                       }});
+    } else {
+      std::printf("skip BackendFast cases: %s\n", err.c_str());
+    }
+  }
   for (auto& c : cases) {
     g_test = c.name;
     const int before = g_failures;
