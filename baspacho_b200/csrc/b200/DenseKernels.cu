@@ -930,8 +930,17 @@ void gemmNT<double>(cudaStream_t st, int batch, int64_t m, int64_t n, int64_t k,
     else
       launchGemmF64<128, 128, 16, 64, 32, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
   }
-  else
-    launchGemmF64<64, 64, 16, 32, 16, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
+  else {
+    // Opt-in experiment for the next round (BSPB200_GEMM_SMALL=1, unmeasured): 64 x 32 tiles (4 warps) when the 64 x 64
+    // grid is between one and two tiles per SM - e.g. the 5000 x 96 x 96 updates of the blocked Cholesky put 158 tiles
+    // on 148 SMs, so ten SMs run two tiles back to back and set the launch's duration; half-size tiles even that out.
+    static const bool smallTiles = getenv("BSPB200_GEMM_SMALL") && atoi(getenv("BSPB200_GEMM_SMALL")) != 0;
+    const int64_t t64 = (int64_t)ceilDiv(m, 64) * ceilDiv(n, 64) * batch;
+    if (smallTiles && t64 > 148 && t64 < 2 * 148)
+      launchGemmF64<64, 32, 16, 32, 16, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
+    else
+      launchGemmF64<64, 64, 16, 32, 16, 4>(st, batch, s, alpha, A, B, beta, C, aligned16);
+  }
 }
 
 template <>
