@@ -24,6 +24,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# stdout carries exactly one JSON line: NCCL's version banner / debug lines go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 sys.path.insert(0, ROOT)
 
 METRIC = "factor()+solve() GF/s (algorithmic fp64 flops of the skeleton / time)"
