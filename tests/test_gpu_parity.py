@@ -413,3 +413,48 @@ def test_ref_cuda_baseline_against_oracle():
         mask = np.tril(r.densify(np.ones_like(data))) > 0
         assert np.abs(r.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
         assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+
+
+def test_full_size_headline_properties():
+    """BASELINE.json's headline configuration at FULL size (BAL-shaped 871 cameras x 527 480 points, 82 M factor entries -
+    too large for the dense / oracle checks above), through size-independent properties: the residual of A x = b computed
+    with the block-sparse product (addMvFrom), linearity of the solve, and run-to-run determinism of factor and solve (the
+    sparse elimination here has no atomics). Same calls and inputs as bench.py's timed step."""
+    import torch
+    from bench import WORKLOADS
+    w = WORKLOADS["bal"]
+    api = bsp.api()
+    sizes, ptrs, inds = api.gen_pattern_arrays(w["kind"], w["params"], w["bsize"][0], w["bsize"][1], 37)
+    s = bsp.Solver.create(sizes, ptrs, inds, [0, w["n_elim"]], computation_model=_capi.MODEL_B200,
+                          find_sparse_elim_ranges=w["auto"])
+    assert s.order == 527480 * 3 + 871 * 6
+    data_h = api.random_data_array(s.data_size, -1, 1, 37)
+    s.damp(data_h, 0.0, s.order * 1.2)
+    pristine = torch.from_numpy(data_h).cuda()
+    b1 = torch.from_numpy(api.random_data_array(s.order, -1, 1, 38).reshape(1, s.order)).cuda()
+    b2 = torch.from_numpy(api.random_data_array(s.order, -1, 1, 39).reshape(1, s.order)).cuda()
+
+    fac = pristine.clone()
+    s.factor(fac)
+    x1 = b1.clone()
+    s.solve(fac, x1)
+    assert bool(torch.isfinite(x1).all())
+    # (1) residual through the block-sparse symmetric product on the UNFACTORED matrix
+    y = torch.zeros_like(b1)
+    s.add_mv_from(pristine, 0, x1, y)
+    torch.cuda.synchronize()
+    assert float((y - b1).norm() / b1.norm()) < 1e-12
+    # (2) linearity: solve(b1 + b2) == solve(b1) + solve(b2)
+    x2, x12 = b2.clone(), (b1 + b2).clone()
+    s.solve(fac, x2)
+    s.solve(fac, x12)
+    assert float((x12 - (x1 + x2)).abs().max() / x12.abs().max()) < 1e-12
+    # (3) determinism: a second factorization and solve of the same input reproduce the first bit for bit
+    fac_b = pristine.clone()
+    s.factor(fac_b)
+    x1_b = b1.clone()
+    s.solve(fac_b, x1_b)
+    torch.cuda.synchronize()
+    # (the upper triangles of the diagonal blocks are don't-care entries of the format: equal or both NaN)
+    assert bool(((fac == fac_b) | (fac.isnan() & fac_b.isnan())).all())
+    assert torch.equal(x1, x1_b)
