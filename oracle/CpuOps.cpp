@@ -141,6 +141,9 @@ struct CpuSymbolicCtx : SymbolicCtx {
   const CoalescedBlockMatrixSkel& skel;
   bool useBlas;
   oracle::ThreadPool pool;
+  // which row-chain variant doElimination runs: 0 = the reference's dispatch rule, 1 = eliminateRowChain,
+  // 2 = eliminateVerySparseRowChain (ORACLE_ELIM_VARIANT, read when the context is created; tests force both)
+  int elimVariant = getenv("ORACLE_ELIM_VARIANT") ? atoi(getenv("ORACLE_ELIM_VARIANT")) : 0;
 };
 
 // ---------------------------------------------------------------- BLAS shims (row-major views)
@@ -259,6 +262,45 @@ struct CpuNumericCtx : NumericCtx<T> {
     }
   }
 
+  // The variant the reference picks when the rows of the elimination rectangle hold few chains each
+  // (eliminateVerySparseRowChain, reference MatOpsCpuBase.h:321-373): per chain found in the row the WHOLE product
+  // (rows from the chain downward) x (chain)^T goes to a reusable buffer, then every block of it is subtracted from
+  // the target column; the target chain is located by bisection over the target column's chainRowSpan (no
+  // span -> chain table to fill), and the diagonal block is subtracted as a full square (its upper triangle is a
+  // don't-care region of the format).
+  void eliminateVerySparseRow(const CpuSymElimCtx& elim, T* data, int64_t sRel, vector<T>& prod) const {
+    if (elim.rowPtr[sRel] == elim.rowPtr[sRel + 1]) return;
+    const int64_t s = sRel + elim.spanRowBegin;
+    const int64_t target = skel.spanToLump[s], tw = skel.lumpSize(target);
+    const int64_t colInTarget = skel.spanStart[s] - skel.lumpStart[target];
+    const int64_t bisectStart = skel.chainColPtr[target], bisectEnd = skel.chainColPtr[target + 1];
+    for (int64_t i = elim.rowPtr[sRel]; i < elim.rowPtr[sRel + 1]; i++) {
+      const int64_t src = elim.colLump[i], k = skel.lumpSize(src);
+      BASPACHO_CHECK_GE(elim.chainColOrd[i], 1);  // there must be a diagonal block
+      const int64_t first = skel.chainColPtr[src] + elim.chainColOrd[i], end = skel.chainColPtr[src + 1];
+      BASPACHO_CHECK_EQ(skel.chainRowSpan[first], s);
+      const int64_t rowsAbove = skel.chainRowsTillEnd[first - 1];
+      const int64_t m = skel.chainRowsTillEnd[first] - rowsAbove;
+      const int64_t rowsOnward = skel.chainRowsTillEnd[end - 1] - rowsAbove;
+      const T* A = data + skel.chainData[first];  // (rowsOnward x k) from the chain downward, first m rows = chain
+      prod.resize((size_t)(rowsOnward * m));
+      for (int64_t r = 0; r < rowsOnward; r++)
+        for (int64_t j = 0; j < m; j++) {
+          T acc = T(0);
+          for (int64_t q = 0; q < k; q++) acc += A[r * k + q] * A[j * k + q];
+          prod[r * m + j] = acc;
+        }
+      for (int64_t c = first; c < end; c++) {
+        const int64_t relRow = skel.chainRowsTillEnd[c - 1] - rowsAbove;
+        const int64_t rows = skel.chainRowsTillEnd[c] - rowsAbove - relRow;
+        const int64_t pos = bisect(skel.chainRowSpan.data() + bisectStart, bisectEnd - bisectStart, skel.chainRowSpan[c]);
+        T* dst = data + skel.chainData[bisectStart + pos] + colInTarget;
+        for (int64_t r = 0; r < rows; r++)
+          for (int64_t j = 0; j < m; j++) dst[r * tw + j] -= prod[(relRow + r) * m + j];
+      }
+    }
+  }
+
   void doElimination(const SymElimCtx& elimData, T* data, int64_t lumpsBegin, int64_t lumpsEnd) override {
     const auto* elim = dynamic_cast<const CpuSymElimCtx*>(&elimData);
     BASPACHO_CHECK_NOTNULL(elim);
@@ -268,12 +310,24 @@ struct CpuNumericCtx : NumericCtx<T> {
       for (int64_t l = b; l < e; l++) factorLumpColumn(data, l);
     });
     int64_t nRows = (int64_t)elim->rowPtr.size() - 1;
-    vector<vector<int64_t>> scratch(pool.numThreads());
-    pool.parallelFor(0, nRows, 5, [&](int64_t b, int64_t e, int slot) {
-      auto& map = scratch[slot];
-      if (map.empty()) map.resize(skel.numSpans());
-      for (int64_t r = b; r < e; r++) eliminateRow(*elim, data, r, map);
-    });
+    // dispatch of the reference's BLAS backend (MatOpsFast.cpp:105-147): rows holding more than 3 chains on average
+    // take the span -> chain table variant, sparser rectangles the bisect + product-buffer one; its naive backend
+    // always runs the former (MatOpsRef.cpp:64-82)
+    const int variant = sym.elimVariant;  // 0 = the reference's rule, 1 / 2 = force (tests)
+    const bool dense = variant == 1 || (variant == 0 && (!sym.useBlas || elim->colLump.size() > 3 * (elim->rowPtr.size() - 1)));
+    if (dense) {
+      vector<vector<int64_t>> scratch(pool.numThreads());
+      pool.parallelFor(0, nRows, 5, [&](int64_t b, int64_t e, int slot) {
+        auto& map = scratch[slot];
+        if (map.empty()) map.resize(skel.numSpans());
+        for (int64_t r = b; r < e; r++) eliminateRow(*elim, data, r, map);
+      });
+    } else {
+      vector<vector<T>> scratch(pool.numThreads());
+      pool.parallelFor(0, nRows, 5, [&](int64_t b, int64_t e, int slot) {
+        for (int64_t r = b; r < e; r++) eliminateVerySparseRow(*elim, data, r, scratch[slot]);
+      });
+    }
   }
 
   void potrf(int64_t n, T* data, int64_t offA) override {

@@ -9,8 +9,9 @@ from oracle import cpu as oracle_cpu
 
 # reference tolerances: tests/CudaFactorTest.cpp:33-42 (abs Frobenius on the lower triangle)
 EPS = {np.float64: (1e-10, 1e-8), np.float32: (1e-5, 5e-5)}
-# tolerance against the CPU oracle, elementwise relative to max|L| (stated fp64 tolerance of the parity claim)
-ORACLE_RTOL = {np.float64: 5e-13, np.float32: 5e-5}
+# tolerance against the CPU oracle, elementwise relative to max|L| (used as ORACLE_RTOL * 20 by the small-problem tests:
+# fp64 -> 256 eps, the stated fp64 parity tolerance, see FACTOR_ULPS below; fp32 -> the reference's own 1e-3-class bar)
+ORACLE_RTOL = {np.float64: 256 * 2.220446049250313e-16 / 20, np.float32: 5e-5}
 
 
 
@@ -59,3 +60,41 @@ def make_data(solver, seed, dtype, damp_factor=1.5):
 def lower_fro_err(solver, data_a, dense_l):
     got = np.tril(solver.densify(np.ascontiguousarray(data_a)).astype(np.float64))
     return np.linalg.norm(got - np.tril(dense_l))
+
+
+# ---- stated fp64 parity tolerance of the product against the CPU oracle: elementwise, in units of
+# eps(fp64) * max|reference|. FACTOR_ULPS covers stored lower-triangle factor entries, SOLVE_ULPS solution entries.
+# Both are set from the errors observed on the B200 at BASELINE sizes (profiles/r02_parity_observed.json) times < 10.
+# Observed at full size (B200, round 2): factor 4 - 30 ulps on configs 1-4, 127 on config 5 (each diagonal camera block
+# there sums ~25 000 pair products, in a different order than the oracle's row-chain loop); solution 30 - 250 ulps.
+EPS64 = 2.220446049250313e-16
+FACTOR_ULPS = 128.0
+FACTOR_ULPS_LONG_SUMS = 512.0   # config 5 only (sums of > 10^4 terms per target entry)
+SOLVE_ULPS = 1024.0
+TOL_FACTOR = 256 * EPS64        # small-problem tests: |L_gpu - L_oracle| <= TOL_FACTOR * max|L|
+TOL_SOLVE = 1024 * EPS64        # |x_gpu - x_oracle| <= TOL_SOLVE * max(1, max|x|)
+
+
+def flat_lower_mask(solver):
+    """boolean mask over the flat factor data: False on the strictly-upper entries of every lump's diagonal block (the
+    don't-care region of the format, reference CoalescedBlockMatrix.h:38-111), True on everything that is stored"""
+    mask = np.ones(solver.data_size, dtype=bool)
+    lump_start = np.asarray(solver.lumpStart)
+    widths = np.diff(lump_start)
+    chain_col_ptr = np.asarray(solver.chainColPtr)
+    offs = np.asarray(solver.chainData)[chain_col_ptr[:-1]]
+    for w in np.unique(widths):
+        if w < 2:
+            continue
+        r, c = np.triu_indices(int(w), 1)
+        rel = (r * int(w) + c).astype(np.int64)
+        sel = offs[widths == w]
+        for i in range(0, len(sel), 1 << 20):
+            mask[(sel[i:i + (1 << 20), None] + rel[None, :]).ravel()] = False
+    return mask
+
+
+def ulp_err(got, ref, mask=None):
+    """max |got - ref| over the masked entries in units of eps * max|ref|"""
+    g, r = (got, ref) if mask is None else (got[mask], ref[mask])
+    return float(np.abs(g.astype(np.float64) - r.astype(np.float64)).max() / (EPS64 * np.abs(r).max()))

@@ -266,7 +266,7 @@ def test_factor_solve_host_end_to_end():
     ref = data.copy()
     o.factor(ref)
     mask = np.tril(g.densify(np.ones_like(data))) > 0
-    assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= H.TOL_FACTOR * np.abs(ref).max()
 
 
 def test_host_end_to_end_wide_lump_and_heavy_destinations():
@@ -286,12 +286,12 @@ def test_host_end_to_end_wide_lump_and_heavy_destinations():
     o.factor(ref)
     o.solve(ref, xr)
     mask = np.tril(g.densify(np.ones_like(data))) > 0
-    assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
-    assert np.abs(x - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+    assert np.abs(g.densify(fac) - o.densify(ref))[mask].max() <= H.TOL_FACTOR * np.abs(ref).max()
+    assert np.abs(x - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max())
     # device-pointer path on the same problem (elimination + blocked dense factorization of the wide lump)
     d = torch_of(data)
     g.factor(d)
-    assert np.abs(g.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(g.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= H.TOL_FACTOR * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("model", [_capi.MODEL_B200, _capi.MODEL_OPENBLAS_I7])
@@ -311,13 +311,13 @@ def test_grid_wide_and_small_lumps(model):
         g.factor(d)
         got = d.cpu().numpy()
         mask = np.tril(g.densify(np.ones_like(data))) > 0
-        assert np.abs(g.densify(got) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
+        assert np.abs(g.densify(got) - o.densify(ref))[mask].max() <= H.TOL_FACTOR * np.abs(ref).max()
     rhs = H.oapi().random_data_array(g.order * 2, -1, 1, 38).reshape(2, g.order)
     x = torch_of(rhs)
     g.solve(d, x)
     xr = rhs.copy()
     o.solve(ref, xr)
-    assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+    assert np.abs(x.cpu().numpy() - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max())
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -382,7 +382,7 @@ def test_chain_solve_batched_wide_lump():
         ref, xr = datas[q].copy(), rhs[q].copy()
         o.factor(ref)
         o.solve(ref, xr)
-        assert np.abs(xs[q].cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+        assert np.abs(xs[q].cpu().numpy() - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max())
 
 
 def test_ref_cuda_baseline_against_oracle():
@@ -411,8 +411,8 @@ def test_ref_cuda_baseline_against_oracle():
         o.factor(ref)
         o.solve(ref, xr)
         mask = np.tril(r.densify(np.ones_like(data))) > 0
-        assert np.abs(r.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= 1e-11 * np.abs(ref).max()
-        assert np.abs(x.cpu().numpy() - xr).max() <= 1e-11 * max(1.0, np.abs(xr).max())
+        assert np.abs(r.densify(d.cpu().numpy()) - o.densify(ref))[mask].max() <= H.TOL_FACTOR * np.abs(ref).max()
+        assert np.abs(x.cpu().numpy() - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max())
 
 
 def test_full_size_headline_properties():

@@ -116,3 +116,30 @@ def test_cost_model_fit_tool_on_committed_timings():
     summary = json.loads(out[:out.index("\nsweep")])
     assert len(summary["fitted_params"]) == 20
     assert summary["median_rel_err"]["potrf"] < 0.1 and summary["median_rel_err"]["syge"] < 0.15
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_elimination_row_variants(dtype, monkeypatch):
+    """The reference's BLAS backend picks between eliminateRowChain and eliminateVerySparseRowChain by
+    colLump.size() > 3 * numRows (MatOpsFast.cpp:105-147, MatOpsCpuBase.h:267-373): both restated variants, forced in
+    turn, and the dispatch itself give the same Schur complement and factor as the dense answer - on a rectangle dense
+    enough for the first rule (BA-shaped) and on one sparse enough for the second (a FLAT + Schur set)."""
+    cases = []
+    sizes, ptrs, inds = H.ba_problem(260, 14, seed=61, window=4)
+    cases.append((sizes, ptrs, inds, [0, 260]))
+    sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_FLAT_SCHUR, [40, 0.2, 600, 0.02], 2, 4, 41)
+    cases.append((sizes, ptrs, inds, []))
+    for ci, (sizes, ptrs, inds, ranges) in enumerate(cases):
+        outs = []
+        for variant in ("0", "1", "2"):
+            monkeypatch.setenv("ORACLE_ELIM_VARIANT", variant)
+            s = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=3)
+            assert s.num_elim_ranges >= 1
+            data = H.make_data(s, 9 + ci, dtype)
+            L = H.dense_cholesky(s.densify(data))
+            s.factor(data)
+            assert H.lower_fro_err(s, data, L) < H.eps2(dtype, s.order)
+            outs.append(np.tril(s.densify(data)))
+        scale = np.abs(outs[0]).max()
+        assert np.abs(outs[1] - outs[2]).max() <= (1e-13 if dtype == np.float64 else 1e-5) * scale
+        assert np.array_equal(outs[0], outs[1]) or np.array_equal(outs[0], outs[2])  # the dispatch ran one of them
