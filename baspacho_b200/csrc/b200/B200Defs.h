@@ -43,6 +43,7 @@ enum KernelClass {
   KC_SOLVE_ELIM,    // elimination-range triangular solves (HBM bound)
   KC_SOLVE_DENSE,   // dense-lump triangular solves / gemv (HBM bound)
   KC_OTHER,
+  KC_LUMP_CHOL,     // tile-DAG Cholesky of a wide lump column (LumpCholKernel.cu; tensor/FMA bound)
   KC_COUNT
 };
 void profileEnable(bool on);
@@ -128,6 +129,10 @@ class DevBuf {
   T* p_ = nullptr;
   size_t n_ = 0;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remembered per (kernel, device), so
+// a process that drives several GPUs (or calls from several threads) sets it wherever the kernel is about to run
+void ensureDynSmem(const void* kernel, size_t bytes);
 
 inline int ceilDiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -62,9 +62,12 @@ void trsmBlock(cudaStream_t st, int batch, int n, int64_t rows, Operand<T> L, in
 template <typename T>
 void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld);
 
-// load counters used by the panel launches issued from this host thread until reset with nullptr (`batch` zeroed ints;
-// needed when lump columns are factored concurrently on several streams)
-void setPanelCounters(int* counters);
+// the same by ONE persistent tile-DAG kernel (LumpCholKernel.cu: TMA-fed DMMA tiles, device-side dependency flags, the
+// chain of diagonal blocks inside dedicated CTAs); fp64, single matrix, n >= lumpCholMinWidth(), even n / ld and a
+// 16-byte aligned base (TMA). Returns false when not eligible - the caller then runs the recursive schedule.
+bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int64_t ld);
+int lumpCholMinWidth();
+int64_t lumpCholDebugRead(void* out, int64_t bytes);
 
 // diagonal Cholesky + triangular solve of many small lump columns in one launch (work list on the device)
 struct WavePanel;

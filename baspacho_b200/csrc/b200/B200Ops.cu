@@ -92,6 +92,14 @@ struct B200SymbolicCtx : SymbolicCtx {
   }
 
   SymElimCtxPtr prepareElimination(int64_t lumpsBegin, int64_t lumpsEnd) override {
+    auto e = makeElimCtx(lumpsBegin, lumpsEnd);
+    elimRegistry.push_back(e.get());  // owned by the Solver, which outlives every numeric/solve context
+    return SymElimCtxPtr(e.release());
+  }
+
+  // plan of the sparse elimination of [lumpsBegin, lumpsEnd) WITHOUT entering it into the registry of the Solver's
+  // ranges (also used for the point chunks of the host-staged pipeline, b200ElimChunkPlans below)
+  std::unique_ptr<B200SymElimCtx> makeElimCtx(int64_t lumpsBegin, int64_t lumpsEnd) {
     auto e = std::make_unique<B200SymElimCtx>();
     e->elimStat.enabled = false;
     ElimPlan& p = e->host;
@@ -122,8 +130,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     for (auto* v : {&p.dstRows, &p.dstCols, &p.rowChainK}) vector<int16_t>().swap(*v);
     for (auto* v : {&p.taskA, &p.taskB}) vector<uint32_t>().swap(*v);
     vector<uint16_t>().swap(p.taskK);
-    elimRegistry.push_back(e.get());  // owned by the Solver, which outlives every numeric/solve context
-    return SymElimCtxPtr(e.release());
+    return e;
   }
 
   NumericCtxBase* createNumericCtxForType(std::type_index tIdx, int64_t tempBufSize, int batchSize) override;
@@ -180,7 +187,6 @@ struct B200SymbolicCtx : SymbolicCtx {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf<int64_t> spanToChainOffset;
-    DevBuf<int> counters;
   };
   std::vector<Lane> lanes;
   cudaEvent_t evLevel = nullptr;
@@ -196,12 +202,7 @@ struct B200SymbolicCtx : SymbolicCtx {
       }
       B200_CUDA(cudaEventCreateWithFlags(&evLevel, cudaEventDisableTiming));
     }
-    for (Lane& ln : lanes)
-      if (ln.counters.size() < (size_t)batch) {
-        B200_CUDA(cudaStreamSynchronize(ln.st));
-        ln.counters.resize(batch);
-        B200_CUDA(cudaMemset(ln.counters.ptr(), 0, batch * sizeof(int)));
-      }
+    (void)batch;  // the panel kernels' load counters are kept per (device, stream): every lane has its own
     if (laneScratch.size() < tempBytesPerLane * lanes.size()) {
       for (Lane& ln : lanes) B200_CUDA(cudaStreamSynchronize(ln.st));
       laneScratch.resize(tempBytesPerLane * lanes.size());
@@ -487,7 +488,6 @@ struct B200NumericCtx : NumericCtx<TT> {
     cudaStream_t st;
     Work<T> temp;
     int64_t* spanToChainOffset;
-    int* counters;
   };
   size_t laneTempBytes() const { return (size_t)std::max<int64_t>(1, tempSize) * batch * sizeof(T); }
   LaneCtx laneCtx(int k) {
@@ -496,7 +496,6 @@ struct B200NumericCtx : NumericCtx<TT> {
     lc.temp.base = (T*)(sym.laneScratch.ptr() + (size_t)k * laneTempBytes());
     lc.temp.stride = tempSize;
     lc.spanToChainOffset = sym.lanes[k].spanToChainOffset.ptr();
-    lc.counters = sym.lanes[k].counters.ptr();
     return lc;
   }
 
@@ -532,9 +531,7 @@ struct B200NumericCtx : NumericCtx<TT> {
 
   void factorLumpColumn(const Mats<T>& m, int64_t l, const LaneCtx* lc = nullptr) {
     const int64_t n = skel.lumpSize(l);
-    if (lc) setPanelCounters(lc->counters);
     potrfTrapezoid<T>(lc ? lc->st : sym.stream, m.batch, n, skel.lumpTotalRows(l) - n, opnd(m, skel.lumpDataOffset(l)), n);
-    if (lc) setPanelCounters(nullptr);
   }
 
   B200SymbolicCtx& sym;
@@ -797,5 +794,18 @@ struct B200Ops : Ops {
 }  // namespace
 
 OpsPtr b200Ops() { return OpsPtr(new B200Ops); }
+
+// Host-staged pipeline (capi.cpp, bspb200_factor_solve_host): elimination plans of consecutive sub-ranges ("chunks") of
+// one elimination range, so that the elimination of a chunk of point columns can start as soon as the chunk has been
+// uploaded. The plans are ordinary elimination contexts (run through NumericCtx::doElimination) but are NOT ranges of
+// the Solver. Running the chunks in order gives a fixed summation order (deterministic; it differs from the one-plan
+// order of factor() in the last bits).
+std::vector<SymElimCtxPtr> b200ElimChunkPlans(SymbolicCtx& sym, const std::vector<int64_t>& bounds) {
+  auto* bs = dynamic_cast<B200SymbolicCtx*>(&sym);
+  BASPACHO_CHECK_NOTNULL(bs);
+  std::vector<SymElimCtxPtr> out;
+  for (size_t i = 0; i + 1 < bounds.size(); i++) out.emplace_back(bs->makeElimCtx(bounds[i], bounds[i + 1]).release());
+  return out;
+}
 
 }  // namespace BaSpaCho

@@ -1,4 +1,5 @@
 // Per-kernel-class event profiler of the B200 backend (see B200Defs.h).
+#include <map>
 #include <mutex>
 #include "B200Defs.h"
 
@@ -32,9 +33,22 @@ State& state() {
   return s;
 }
 const char* kNames[KC_COUNT] = {"gemm",     "potrf_block", "trsm_block",  "elim_factor", "elim_gather",
-                                "assemble", "solve_elim",  "solve_dense", "other"};
+                                "assemble", "solve_elim",  "solve_dense", "other",       "lump_chol"};
 
 }  // namespace
+
+void ensureDynSmem(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[{kernel, dev}];
+  if (have >= bytes) return;
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  have = bytes;
+}
 
 void profileEnable(bool on) { state().enabled = on; }
 bool profileEnabled() { return state().enabled; }

@@ -8,6 +8,9 @@
 //   potrfTrapezoid - recursive blocked Cholesky of a whole lump column (diagonal block + rows below)
 //   trsmAny        - blocked X L^T = B for any size
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <type_traits>
 #include "B200Kernels.h"
 #include "B200Wave.h"
 
@@ -844,8 +847,7 @@ double gemmFlops(int64_t m, int64_t n, int64_t k, bool lowerOnly) {
 
 template <typename KernelT>
 void setSmem(KernelT kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
-    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  ensureDynSmem((const void*)kernel, bytes);  // per (kernel, device), see B200Defs.h
 }
 
 // Programmatic dependent launch of the dense-factorization chain (panel -> trailing GEMM -> panel ...): every kernel
@@ -878,13 +880,11 @@ void launchGemmF64(cudaStream_t st, int batch, const GemmShape& s, double alpha,
   dim3 grid(ceilDiv(s.n, BN), ceilDiv(s.m, BM), batch);
   if (aligned16) {
     auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 2, MINB>;
-    static bool once = (setSmem(kern, smem), true);
-    (void)once;
+    setSmem(kern, smem);
     launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
   } else {
     auto kern = gemm_nt_f64_kernel<BM, BN, BK, WM, WN, STAGES, 1, MINB>;
-    static bool once = (setSmem(kern, smem), true);
-    (void)once;
+    setSmem(kern, smem);
     launchChain(kern, grid, NT, smem, st, s, alpha, A, B, beta, C);
   }
   B200_LAUNCH_CHECK();
@@ -964,22 +964,30 @@ int maxBlockDim<float>() {
   return kNB;
 }
 
-// zero-initialised load counters of the panel kernel (grow-only; the kernel leaves them zero again)
-// per-lane override of the load counters (concurrent lump columns on different streams must not share them):
-// set by the caller around potrfTrapezoid; the buffer holds `batch` zero-initialised ints and is left zeroed
-static thread_local int* tlsPanelCtr = nullptr;
-void setPanelCounters(int* counters) { tlsPanelCtr = counters; }
-static int* panelCounters(int64_t needed) {
-  static int* buf = nullptr;
-  static int64_t cap = 0;
-  if (needed > cap) {
-    B200_CUDA(cudaDeviceSynchronize());
-    if (buf) cudaFree(buf);
-    cap = std::max<int64_t>(needed, 1 << 16);
-    B200_CUDA(cudaMalloc((void**)&buf, cap * sizeof(int)));
-    B200_CUDA(cudaMemset(buf, 0, cap * sizeof(int)));
+// Zero-initialised load counters of the panel kernels' writer election (the kernels leave them zero again), one buffer
+// per (device, stream): launches on one stream run in order, so they can share counters; launches on different streams -
+// the lanes of concurrent lump columns, other Solvers, other host threads - and on different devices never do.
+// (The reference keeps its library handles per symbolic context, MatOpsCuda.cu:55-76; keying by the stream a context
+// was given covers direct bspb200_dev_* calls as well.)
+static int* panelCounters(cudaStream_t st, int64_t needed) {
+  struct Buf {
+    int* ptr = nullptr;
+    int64_t cap = 0;
+  };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[{dev, st}];
+  if (needed > b.cap) {
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (b.ptr) cudaFree(b.ptr);
+    b.cap = std::max<int64_t>(needed, 1 << 12);
+    B200_CUDA(cudaMalloc((void**)&b.ptr, b.cap * sizeof(int)));
+    B200_CUDA(cudaMemsetAsync(b.ptr, 0, b.cap * sizeof(int), st));
   }
-  return buf;
+  return b.ptr;
 }
 
 // phase time stamps of the panel kernel (diagnostics, off unless BSPB200_PANEL_CLK is set)
@@ -995,6 +1003,7 @@ static long long* panelClockBuf() {
   return buf;
 }
 int64_t debugRead(int what, void* out, int64_t bytes) {
+  if (what == 1) return lumpCholDebugRead(out, bytes);
   if (what == 0 && panelClockBuf()) {
     const int64_t n = std::min<int64_t>(bytes, 64 * sizeof(long long));
     B200_CUDA(cudaDeviceSynchronize());
@@ -1022,8 +1031,7 @@ static int panelUF() {
 template <typename T, int UF>
 static void launchPanel2UF(cudaStream_t st, dim3 grid, int n, int64_t rows, Operand<T> L, int64_t ldl, Operand<T> B,
                            int64_t ldb, const WavePanel* work, int* counters, int lumpsInLaunch, long long* clk) {
-  static bool once = (setSmem(panel2_kernel<T, UF>, panel2Smem<T>()), true);
-  (void)once;
+  setSmem(panel2_kernel<T, UF>, panel2Smem<T>());
   launchChain(panel2_kernel<T, UF>, grid, kPanelThreads, panel2Smem<T>(), st, n, rows, L, ldl, B, ldb, work, counters,
               lumpsInLaunch, clk);
   B200_LAUNCH_CHECK();
@@ -1048,14 +1056,13 @@ static void launchPanel(cudaStream_t st, int batch, int n, int64_t rows, Operand
   int ctas = std::max(1, ceilDiv(rows, kPanelRows));
   if (DO_POTRF && panelVersion() == 2) {
     launchPanel2<T>(st, dim3(ctas, 1, batch), n, rows, L, ldl, B, ldb, nullptr,
-                    tlsPanelCtr ? tlsPanelCtr : panelCounters(batch), 1, panelClockBuf());
+                    panelCounters(st, batch), 1, panelClockBuf());
     return;
   }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
-  static bool once = (setSmem(panel_kernel<T, DO_POTRF>, smem), true);
-  (void)once;
+  setSmem(panel_kernel<T, DO_POTRF>, smem);
   panel_kernel<T, DO_POTRF><<<dim3(ctas, 1, batch), kPanelThreads, smem, st>>>(n, rows, L, ldl, B, ldb, nullptr,
-                                                                               tlsPanelCtr ? tlsPanelCtr : panelCounters(batch),
+                                                                               panelCounters(st, batch),
                                                                                1, panelClockBuf());
   B200_LAUNCH_CHECK();
 }
@@ -1069,14 +1076,13 @@ void potrfTrsmPanelBatch(cudaStream_t st, int batch, Operand<T> data, const Wave
   ProfScope prof(st, KC_POTRF_BLOCK, flops * batch, 0);
   if (panelVersion() == 2) {
     launchPanel2<T>(st, dim3((unsigned)count, 1, batch), 0, 0, data, 0, data, 0, work,
-                    panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
+                    panelCounters(st, (int64_t)batch * numLumps), numLumps, nullptr);
     return;
   }
   size_t smem = ((size_t)kNB * kLDT + kNB + (size_t)kPanelRows * kLDX) * sizeof(T);
-  static bool once = (setSmem(panel_kernel<T, true>, smem), true);
-  (void)once;
+  setSmem(panel_kernel<T, true>, smem);
   panel_kernel<T, true><<<dim3((unsigned)count, 1, batch), kPanelThreads, smem, st>>>(
-      0, 0, data, 0, data, 0, work, panelCounters((int64_t)batch * numLumps), numLumps, nullptr);
+      0, 0, data, 0, data, 0, work, panelCounters(st, (int64_t)batch * numLumps), numLumps, nullptr);
   B200_LAUNCH_CHECK();
 }
 template void potrfTrsmPanelBatch<double>(cudaStream_t, int, Operand<double>, const WavePanel*, int64_t, int, double);
@@ -1102,36 +1108,6 @@ static void potrfTrsmPanel(cudaStream_t st, int batch, int n, int64_t rows, Oper
                            int64_t ldb) {
   ProfScope prof(st, KC_POTRF_BLOCK, ((double)n * n * n / 3 + (double)rows * n * n) * batch, 0);
   launchPanel<T, true>(st, batch, n, rows, L, ldl, B, ldb);
-}
-
-// side stream + events of the lookahead schedule (one per process; a Solver is driven by one host thread)
-struct Lookahead {
-  cudaStream_t side = nullptr;
-  cudaEvent_t evPanel = nullptr, evPart2 = nullptr, evStart = nullptr, evDone = nullptr;
-};
-static Lookahead& lookahead() {
-  static Lookahead la = [] {
-    Lookahead l;
-    int lo = 0, hi = 0;
-    B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    B200_CUDA(cudaStreamCreateWithPriority(&l.side, cudaStreamNonBlocking, hi));  // greatest priority
-    B200_CUDA(cudaEventCreateWithFlags(&l.evStart, cudaEventDisableTiming));
-    B200_CUDA(cudaEventCreateWithFlags(&l.evDone, cudaEventDisableTiming));
-    B200_CUDA(cudaEventCreateWithFlags(&l.evPanel, cudaEventDisableTiming));
-    B200_CUDA(cudaEventCreateWithFlags(&l.evPart2, cudaEventDisableTiming));
-    return l;
-  }();
-  return la;
-}
-static int& lookaheadMode() {
-  static int mode = [] {
-    // 0 (default): recursive blocked schedule on the caller's stream. 1: right-looking depth-1 lookahead on an
-    // internal high-priority stream (measured ~1% on the BAL-shaped benchmark: the panel chain, not the overlap,
-    // bounds the critical path); 2: the lookahead schedule serialised on one stream (debug)
-    const char* e = getenv("BSPB200_LOOKAHEAD");
-    return e ? atoi(e) : 0;
-  }();
-  return mode;
 }
 
 // Recursive blocked Cholesky of the (n + rowsBelow) x n trapezoid (row-major, ld). Columns [c0, c0 + w):
@@ -1175,43 +1151,13 @@ static void potrfRec(cudaStream_t st, int batch, int64_t totalRows, int64_t c0, 
 template <typename T>
 void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Operand<T> A, int64_t ld) {
   if (n <= 0) return;
-  if (lookaheadMode() == 0 || n <= 2 * kNB) {
-    potrfRec<T>(st, batch, n + rowsBelow, 0, n, A, ld);
-    return;
+  if constexpr (std::is_same<T, double>::value) {
+    // wide single-matrix lumps: one persistent tile-DAG kernel instead of the launch sequence below
+    if (batch == 1 && !A.many && lumpCholesky(st, n, rowsBelow, A.at(0), ld)) return;
   }
-  // Right-looking over 96-column panels with a depth-1 lookahead: the trailing update of panel k is split into
-  //   part 1 = block column k+1 (what panel k+1 needs), on the caller's stream, and
-  //   part 2 = every later column, on a low-priority side stream,
-  // so the latency-bound panel k+1 (diagonal Cholesky + triangular solve) runs while part 2 of panel k keeps the
-  // tensor pipes busy. Dependencies: part2(k) waits for panel(k) (event); part1(k+1) waits for part2(k) (event).
-  Lookahead& la = lookahead();
-  const int64_t total = n + rowsBelow, nb = kNB;
-  // high priority: panels + part 1 (the critical path); part 2 stays on the caller's stream
-  cudaStream_t crit = lookaheadMode() == 2 ? st : la.side;  // mode 2 (debug): same schedule serialised on one stream
-  B200_CUDA(cudaEventRecord(la.evStart, st));
-  B200_CUDA(cudaStreamWaitEvent(crit, la.evStart, 0));
-  bool pendingP2 = false;
-  for (int64_t j0 = 0; j0 < n; j0 += nb) {
-    const int64_t jb = std::min<int64_t>(nb, n - j0), r0 = j0 + jb;
-    Operand<T> diag = shifted(A, j0 * ld + j0);
-    potrfTrsmPanel<T>(crit, batch, (int)jb, total - r0, diag, ld, shifted(A, r0 * ld + j0), ld);
-    if (r0 >= n) break;
-    const int64_t jb2 = std::min<int64_t>(nb, n - r0), r1 = r0 + jb2;
-    if (r1 < n) B200_CUDA(cudaEventRecord(la.evPanel, crit));
-    if (pendingP2) B200_CUDA(cudaStreamWaitEvent(crit, la.evPart2, 0));
-    Operand<T> P = shifted(A, r0 * ld + j0);
-    gemmNT<T>(crit, batch, total - r0, jb2, jb, T(-1), P, ld, P, ld, T(1), shifted(A, r0 * ld + r0), ld, true);
-    pendingP2 = false;
-    if (r1 < n) {
-      B200_CUDA(cudaStreamWaitEvent(st, la.evPanel, 0));
-      Operand<T> P2 = shifted(A, r1 * ld + j0);
-      gemmNT<T>(st, batch, total - r1, n - r1, jb, T(-1), P2, ld, P2, ld, T(1), shifted(A, r1 * ld + r1), ld, true);
-      B200_CUDA(cudaEventRecord(la.evPart2, st));
-      pendingP2 = true;
-    }
-  }
-  B200_CUDA(cudaEventRecord(la.evDone, crit));
-  B200_CUDA(cudaStreamWaitEvent(st, la.evDone, 0));
+  // (A right-looking depth-1 lookahead on a priority stream was measured in round 1 and removed: a panel launched behind
+  // a GEMM that owns every SM waits for whole SMs to drain. The tile-DAG kernel above overlaps the chain instead.)
+  potrfRec<T>(st, batch, n + rowsBelow, 0, n, A, ld);
 }
 
 template <typename T>

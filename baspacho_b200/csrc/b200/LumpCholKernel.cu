@@ -1,0 +1,810 @@
+// Blocked Cholesky of ONE wide lump column (diagonal block n x n + the rows below it) as a single persistent kernel:
+// a left-looking tile DAG with device-side dependency flags, hand-written for sm_100a.
+//
+// Replaces, for wide supernodes, the reference's cusolverDn<t>potrf + cublas<t>trsm on a lump column
+// (MatOpsCuda.cu:508-566) and this backend's own recursive schedule (DenseKernels.cu potrfRec: ~55 panel launches +
+// ~54 GEMM launches in series for the 5226-wide camera lump of the BAL-shaped problem, nothing overlapping).
+//
+// The (n + rowsBelow) x n trapezoid is cut into 96 x 96 tiles. Tile (i, c), i > c, is finished in one go:
+//     L(i,c) = ( A(i,c) - sum_{k<c} L(i,k) L(c,k)^T ) W_c^T ,     W_c = L(c,c)^-1 ,
+// the sum running over the already finished tiles of block rows i and c (left-looking: every tile is read-modify-
+// written exactly once, its accumulator lives in registers for the whole sum). Jobs are handed out by an arrival
+// ticket in column-major order, so a job only ever waits for jobs with smaller tickets, which are finished or being
+// executed by resident CTAs: no deadlock whatever the number of co-resident CTAs. A finished tile is published with
+// store -> fence -> release-store of the launch's epoch into its flag; the loader polls the flags of the two tiles
+// of a K block with acquire loads before requesting them.
+//
+// The critical path of a blocked Cholesky is the chain of diagonal blocks. Here block d is a special job that owns
+// the pair (d, d-1), (d, d): it accumulates both tiles in one 96 x 192 product while the previous diagonal block is
+// still being factored, and when W_{d-1} is published only   L(d,d-1) = M W^T  ->  D -= L(d,d-1) L(d,d-1)^T  ->
+// potrf(D)  ->  W_d   remain, all inside the CTA (one flag hop per block column instead of kernel boundaries).
+// Everything else - the bulk of the flops - fills the other SMs in the shadow of that chain.
+//
+// Data path: operand tiles travel HBM/L2 -> shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, one
+// elected producer thread, full/empty mbarrier ring of 4 stages), the contraction runs on the fp64 tensor pipe
+// (mma.sync.m8n8k4.f64 = DMMA; tcgen05.mma has no f64 kind), accumulators in registers. The diagonal 96 x 96
+// Cholesky is the register-resident right-looking scheme of panel2_kernel (4 columns per step, branch-free rsqrt).
+//
+// Determinism: the summation order of every entry is fixed (k ascending), independent of the schedule.
+// Non-SPD input: a non-positive pivot yields NaN, which propagates; flags are still published, nothing hangs.
+// Every spin loop is bounded: on timeout the kernel raises the abort flag, stops waiting and poisons A[0] with NaN.
+#include <cuda.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include "B200Kernels.h"
+
+namespace BaSpaCho {
+namespace b200 {
+namespace {
+
+constexpr int TB = 96;                 // tile edge
+constexpr int BK = 16;                 // K per pipeline stage: 16 doubles = 128 bytes = the swizzle span
+constexpr int NST = 4;                 // pipeline stages
+constexpr int kConsumers = 256;        // 8 MMA warps; lane 0 of warp 0 doubles as the TMA producer (a ninth warp would
+constexpr int kThreads = kConsumers;   // round the CTA up to 12 warps of registers: 168 per thread instead of 255)
+constexpr int kTileBytes = TB * BK * 8;    // 12288: one 96-row operand tile of a stage
+constexpr int kStageBytes = 3 * kTileBytes;  // A (96 rows) + B (up to 192 rows)
+constexpr int LDE = 100;               // row stride (doubles) of the epilogue operands: [row][k], conflict-free fragments
+constexpr int LDQ = 97;                // row stride of the diagonal block staging (odd: lanes walking down rows)
+constexpr int kSmemE0 = 0;                            // [96][LDE]  M / L(d,d-1)            76800 B
+constexpr int kSmemE1 = TB * LDE * 8;                 // [96][LDE]  W^T operand / [96][LDQ] diagonal block
+constexpr int kSmemCol = 2 * TB * LDE * 8;            // [4][96] raw columns of the potrf step
+constexpr int kSmemY = kSmemCol + 4 * TB * 8;         // [96][4] finished rows of the potrf step
+constexpr int kSmemT = kSmemY + 4 * TB * 8;           // [2][32][LDE] scratch of the blocked inversion      51200 B
+constexpr int kSmemBar = kSmemT + 2 * 32 * LDE * 8;   // mbarriers
+constexpr int kSmemBytes = kSmemBar + 128 + 1024;     // + alignment slack
+static_assert(NST * kStageBytes <= kSmemCol, "the pipeline stages alias the epilogue buffers");
+
+struct LcParams {
+  double* A;
+  int64_t ld;
+  int n, rows;          // lump width, total rows (n + rowsBelow)
+  int nbc, nbr;         // block columns / block rows
+  int numJobs;
+  unsigned* done;       // [nbr * nbc] tile flags (epoch valued)
+  unsigned* wdone;      // [nbc] inverse flags
+  unsigned* ticket;
+  unsigned* abortFlag;  // holds the epoch of the launch that timed out (never reset)
+  double* wbuf;         // [nbc][96 * 96] block inverses, row-major
+  unsigned epoch, ticketBase;
+  long long* dbg;       // diagnostics (BSPB200_LUMPCHOL_DBG=1): [64][16] clock64 stamps of the diagonal jobs, then
+                        // [gridDim.x][4] per-CTA cycle totals (main loop, epilogue, flag waits of the producer, jobs)
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbarArriveExpectTx(uint32_t bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+  while (!mbarTryWait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tmaLoad2D(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ldAcquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stRelease(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumerBar() { __syncthreads(); }
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double rsqrtNewton(double x) {  // see DenseKernels.cu rsqrtFast
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// bounded wait for a flag to reach `epoch`; returns false after the abort flag was raised (by us or anybody)
+__device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, unsigned* abortFlag) {
+  unsigned spins = 0;
+  while (ldAcquire(flag) != epoch) {
+    if ((++spins & 63u) == 0) {
+      if (*(volatile unsigned*)abortFlag == epoch) return false;
+      if (spins > (1u << 24)) {
+        atomicExch(abortFlag, epoch);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ diagonal block
+// In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the nd x nd lower triangle) by the 256 consumer
+// threads: thread (warp w, lane l) owns rows l + 32 a (a < 3) x columns w + 8 u (u < 12) in registers; four columns per
+// step and two barriers (the scheme of panel2_kernel, DenseKernels.cu, without slab rows).
+__device__ __forceinline__ void potrfTile(double* S, int nd, double* colbuf, double* ybuf, int warp, int lane) {
+  constexpr int NW = 8, RA = 3, CU = 12;
+  double reg[RA][CU];
+#pragma unroll
+  for (int a = 0; a < RA; a++)
+#pragma unroll
+    for (int u = 0; u < CU; u++) reg[a][u] = S[(lane + 32 * a) * LDQ + warp + NW * u];
+#pragma unroll
+  for (int u = 0; u < CU; u++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int j0 = NW * u + 4 * h;
+      if (j0 < nd) {
+        const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
+        if (q >= 0 && q < 4) {
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (lane + 32 * a >= j0) colbuf[q * TB + lane + 32 * a] = reg[a][u];
+        }
+        consumerBar();
+        double d[4][4], raw[RA][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+          for (int r = c; r < 4; r++) d[r][c] = colbuf[c * TB + j0 + r];
+#pragma unroll
+        for (int a = 0; a < RA; a++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) raw[a][c] = (32 * a + 31 < j0) ? 0.0 : colbuf[c * TB + lane + 32 * a];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (j0 + c >= nd) d[c][c] = 1.0;  // columns beyond the block act as identity
+        double rs[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+          for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
+          rs[c] = rsqrtNewton(d[c][c]);
+#pragma unroll
+          for (int r = c + 1; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
+            d[r][c] *= rs[c];
+          }
+        }
+        double y[RA][4];
+#pragma unroll
+        for (int a = 0; a < RA; a++) {
+          const int t = lane + 32 * a - j0;
+          if (32 * a + 31 < j0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) y[a][c] = 0.0;
+            continue;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            double v = raw[a][c];
+#pragma unroll
+            for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
+            y[a][c] = (t >= c) ? v * rs[c] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < RA; a++)
+          if (warp == a) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
+          }
+        consumerBar();
+#pragma unroll
+        for (int sl = u; sl < CU; sl++) {
+          const int cb = NW * sl;
+          const double2 lo = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4);
+          const double2 hi = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4 + 2);
+          double yc[4] = {lo.x, lo.y, hi.x, hi.y};
+          if (sl == u && !(h == 0 && warp >= 4)) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) yc[c] = 0.0;
+          }
+#pragma unroll
+          for (int a = 0; a < RA; a++) {
+            if (j0 + 3 < 32 * a + 31 && cb <= 32 * a + 31) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) reg[a][sl] -= y[a][c] * yc[c];
+            }
+          }
+        }
+        if (q >= 0 && q < 4) {
+#pragma unroll
+          for (int a = 0; a < RA; a++)
+            if (lane + 32 * a >= j0) reg[a][u] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+        }
+      }
+    }
+  }
+  consumerBar();
+#pragma unroll
+  for (int u = 0; u < CU; u++)
+#pragma unroll
+    for (int a = 0; a < RA; a++) S[(lane + 32 * a) * LDQ + warp + NW * u] = reg[a][u];
+  consumerBar();
+}
+
+// dst(32 x 32, ldd) = sign * X(32 x 32, ldx) * Y(32 x 32, ldy) (+ dst when ACC), 256 threads: thread -> row tid / 8,
+// 4 consecutive columns
+template <bool ACC>
+__device__ __forceinline__ void mm32(double* dst, int ldd, const double* X, int ldx, const double* Y, int ldy,
+                                     double sign, int tid) {
+  const int r = tid >> 3, c4 = (tid & 7) * 4;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 8
+  for (int q = 0; q < 32; q++) {
+    const double x = X[r * ldx + q];
+    const double* y = Y + q * ldy + c4;
+    a0 += x * y[0], a1 += x * y[1], a2 += x * y[2], a3 += x * y[3];
+  }
+  double* d = dst + r * ldd + c4;
+  if (ACC) {
+    d[0] += sign * a0, d[1] += sign * a1, d[2] += sign * a2, d[3] += sign * a3;
+  } else {
+    d[0] = sign * a0, d[1] = sign * a1, d[2] = sign * a2, d[3] = sign * a3;
+  }
+}
+
+// W = L^-1 for the lower-triangular L in S ([96][LDQ], identity beyond nd) -> Wm ([96][LDE], zero above the diagonal),
+// blocked 3 x 3 over 32 x 32 blocks: the three diagonal inverses by forward substitution (one warp each, thread per
+// column), then W21 = -W22 (L21 W11), W32 = -W33 (L32 W22), W31 = -W33 (L31 W11 + L32 W21) with all 256 threads.
+// T ([32][LDE] x 2) is scratch.
+__device__ __forceinline__ void invertTile(const double* S, double* Wm, double* T, int tid, int warp, int lane) {
+  for (int i = tid; i < TB * LDE; i += kConsumers) Wm[i] = 0.0;
+  consumerBar();
+  if (warp < 3) {
+    const int b0 = 32 * warp, c = lane;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < i; q++) s -= S[(b0 + i) * LDQ + b0 + q] * w[q];
+      w[i] = (i >= c) ? s / S[(b0 + i) * LDQ + b0 + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) Wm[(b0 + i) * LDE + b0 + c] = w[i];
+  }
+  consumerBar();
+  double* T0 = T;
+  double* T1 = T + 32 * LDE;
+  // T0 = L21 W11, T1 = L32 W22
+  mm32<false>(T0, LDE, S + 32 * LDQ, LDQ, Wm, LDE, 1.0, tid);
+  mm32<false>(T1, LDE, S + 64 * LDQ + 32, LDQ, Wm + 32 * LDE + 32, LDE, 1.0, tid);
+  consumerBar();
+  // W21 = -W22 T0, W32 = -W33 T1
+  mm32<false>(Wm + 32 * LDE, LDE, Wm + 32 * LDE + 32, LDE, T0, LDE, -1.0, tid);
+  mm32<false>(Wm + 64 * LDE + 32, LDE, Wm + 64 * LDE + 64, LDE, T1, LDE, -1.0, tid);
+  consumerBar();
+  // T0 = L31 W11 + L32 W21
+  mm32<false>(T0, LDE, S + 64 * LDQ, LDQ, Wm, LDE, 1.0, tid);
+  consumerBar();
+  mm32<true>(T0, LDE, S + 64 * LDQ + 32, LDQ, Wm + 32 * LDE, LDE, 1.0, tid);
+  consumerBar();
+  // W31 = -W33 T0
+  mm32<false>(Wm + 64 * LDE, LDE, Wm + 64 * LDE + 64, LDE, T0, LDE, -1.0, tid);
+  consumerBar();
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// job t (column-major): t = 0 -> diagonal block 0; then for c = 0 .. nbc-1 the rows i = c+1 .. nbr-1 of block column
+// c; (c+1, c) with c+1 < nbc is the diagonal job of block c+1 (tiles (c+1,c) and (c+1,c+1)).
+struct Job {
+  int i, c, diag;  // diag: this job also owns the diagonal tile (i, i)
+};
+__device__ __forceinline__ Job decodeJob(int t, int nbc, int nbr) {
+  Job j;
+  if (t == 0) {
+    j.i = 0, j.c = -1, j.diag = 1;
+    return j;
+  }
+  int rem = t - 1, c = 0;
+  while (rem >= nbr - c - 1) rem -= nbr - c - 1, c++;
+  j.c = c, j.i = c + 1 + rem;
+  j.diag = (rem == 0 && c + 1 < nbc) ? 1 : 0;
+  return j;
+}
+
+// what the producer lane needs to request the operand tiles of a job
+struct LoadCtx {
+  const CUtensorMap* tmap;
+  const unsigned* doneA;  // flags of block row i
+  const unsigned* doneB;  // flags of block row c
+  unsigned* abortFlag;
+  unsigned epoch;
+  int rowA0, rowB0, nBTiles;
+  bool ok;  // false once the launch was aborted: stop waiting for flags, keep the pipeline protocol going
+};
+__device__ __forceinline__ void issueStage(LoadCtx& lc, int kt, unsigned q, uint32_t stagesBase, uint32_t fullBar0,
+                                           uint32_t emptyBar0) {
+  const unsigned stage = q % NST, parity = (q / NST) & 1;
+  mbarWait(emptyBar0 + 8 * stage, parity ^ 1);  // every warp released the previous use of the slot
+  if (kt % (TB / BK) == 0 && lc.ok) {           // first stage of a K block: its two source tiles must be published
+    const int kb = kt / (TB / BK);
+    lc.ok = waitFlag(lc.doneA + kb, lc.epoch, lc.abortFlag) && waitFlag(lc.doneB + kb, lc.epoch, lc.abortFlag);
+    fenceProxyAsync();  // the tiles were written through the generic proxy, TMA reads through the async proxy
+  }
+  const uint32_t bar = fullBar0 + 8 * stage, dst = stagesBase + stage * kStageBytes;
+  mbarArriveExpectTx(bar, kTileBytes * (1 + lc.nBTiles));
+  tmaLoad2D(dst, lc.tmap, kt * BK, lc.rowA0, bar);
+  tmaLoad2D(dst + kTileBytes, lc.tmap, kt * BK, lc.rowB0, bar);
+  if (lc.nBTiles == 2) tmaLoad2D(dst + 2 * kTileBytes, lc.tmap, kt * BK, lc.rowB0 + TB, bar);
+}
+
+template <int TN>  // column tiles per warp: 6 (one 96-wide tile, warps 4 x 2 of 24 x 48) or 12 (two tiles, 24 x 96)
+__device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int kTiles, uint32_t stagesBase, uint32_t fullBar0,
+                                         uint32_t emptyBar0, unsigned& it, int rowA, int rowB, int g, int t, int lane,
+                                         bool producer, LoadCtx& lc) {
+  // swizzled position of this lane's fragment element inside a 128-byte row: 16-byte chunk (k >> 1) ^ (row & 7)
+  uint32_t koff[BK / 4];
+#pragma unroll
+  for (int s = 0; s < BK / 4; s++) koff[s] = ((uint32_t)(((2 * s) | (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
+  if (producer)
+    for (int kt = 0; kt < NST - 1 && kt < kTiles; kt++) issueStage(lc, kt, it + kt, stagesBase, fullBar0, emptyBar0);
+  for (int kt = 0; kt < kTiles; kt++, it++) {
+    const unsigned stage = it % NST, parity = (it / NST) & 1;
+    mbarWait(fullBar0 + 8 * stage, parity);
+    const uint32_t as = stagesBase + stage * kStageBytes + (uint32_t)(rowA + g) * 128;
+    const uint32_t bs = stagesBase + stage * kStageBytes + kTileBytes + (uint32_t)(rowB + g) * 128;
+#pragma unroll
+    for (int s = 0; s < BK / 4; s++) {
+      double af[3], bf[TN];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(af[i]) : "r"(as + i * 8 * 128 + koff[s]));
+#pragma unroll
+      for (int j = 0; j < TN; j++)
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bf[j]) : "r"(bs + j * 8 * 128 + koff[s]));
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbarArrive(emptyBar0 + 8 * stage);
+    // the slot of iteration kt - 1 is requested again for iteration kt + NST - 1
+    if (producer && kt + NST - 1 < kTiles) issueStage(lc, kt + NST - 1, it + NST - 1, stagesBase, fullBar0, emptyBar0);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_constant__ CUtensorMap tmap, LcParams p) {
+  extern __shared__ __align__(1024) unsigned char smemRawLc[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smemRawLc + 1023) & ~(uintptr_t)1023);
+  double* E0 = reinterpret_cast<double*>(smem + kSmemE0);
+  double* E1 = reinterpret_cast<double*>(smem + kSmemE1);
+  double* colbuf = reinterpret_cast<double*>(smem + kSmemCol);
+  double* ybuf = reinterpret_cast<double*>(smem + kSmemY);
+  const uint32_t stagesBase = smemU32(smem);
+  const uint32_t fullBar0 = smemU32(smem + kSmemBar), emptyBar0 = fullBar0 + 8 * NST;
+  __shared__ int jobS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = tid == 0;
+  const int g = lane >> 2, t = lane & 3;
+  // consumer warps: 4 x 2. wn = warp >> 2, so that each column half (the T1 warps, the T2 warps of a diagonal job, which
+  // work alone in parts of its epilogue) has one warp on every SM sub-partition (warp id mod 4) - with wn = warp & 1 the
+  // four warps of a half share two sub-partitions and the DMMA rate of those phases halves
+  const int wm = warp & 3, wn = warp >> 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbarInit(fullBar0 + 8 * s, 1);
+      mbarInit(emptyBar0 + 8 * s, kConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+#define LC_STAMP(i) \
+  if (p.dbg && tid == 0 && job.diag && bi < 64) p.dbg[bi * 16 + (i)] = clock64();
+  long long cycMain = 0, cycEpi = 0, nJobs = 0;
+  unsigned it = 0;  // pipeline iteration counter, continues across the jobs of this CTA (producer and consumers agree)
+  double* __restrict__ A = p.A;
+  const int64_t ld = p.ld;
+
+  for (;;) {
+    if (tid == 0) jobS = (int)(atomicAdd(p.ticket, 1u) - p.ticketBase);
+    __syncthreads();
+    const int jt = jobS;
+    if (jt >= p.numJobs) break;
+    const Job job = decodeJob(jt, p.nbc, p.nbr);
+    const int c = job.c, bi = job.i;
+    const int kTiles = c > 0 ? c * (TB / BK) : 0;  // K = 96 c
+    const int rowA0 = bi * TB, rowB0 = (c < 0 ? 0 : c) * TB;
+
+    const long long tJob = clock64();
+    LC_STAMP(0)
+    double acc[3][12][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 12; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    LoadCtx lc;
+    lc.tmap = &tmap, lc.doneA = p.done + (int64_t)bi * p.nbc, lc.doneB = p.done + (int64_t)(c < 0 ? 0 : c) * p.nbc;
+    lc.abortFlag = p.abortFlag, lc.epoch = p.epoch, lc.rowA0 = rowA0, lc.rowB0 = rowB0, lc.nBTiles = job.diag ? 2 : 1;
+    lc.ok = *(volatile unsigned*)p.abortFlag != p.epoch;
+    if (job.diag)
+      mainLoop<12>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 96 * wn, g, t, lane, producer, lc);
+    else
+      mainLoop<6>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane, producer, lc);
+    __syncthreads();  // (A) every stage has been consumed: the stage memory becomes the epilogue workspace
+    const long long tMain = clock64();
+    LC_STAMP(1)
+
+    const int nc = c >= 0 ? min(TB, p.n - c * TB) : 0;  // valid columns of block column c
+    const bool aborted = *(volatile unsigned*)p.abortFlag == p.epoch;
+
+    if (!job.diag) {
+      // ---- regular tile: M = A(i,c) - acc -> E0 ; W_c -> E1 ; X = M W^T -> global
+      const int rbase = 24 * wm, cbase = 48 * wn;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const int64_t gr = (int64_t)rowA0 + r;
+          double2 a = make_double2(0.0, 0.0);
+          if (gr < p.rows && cc < nc) a = *reinterpret_cast<const double2*>(A + gr * ld + c * TB + cc);
+          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
+        }
+      if (tid == 0 && !aborted) waitFlag(p.wdone + c, p.epoch, p.abortFlag);
+      consumerBar();
+      {
+        const double* __restrict__ W = p.wbuf + (int64_t)c * TB * TB;
+        for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
+          const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
+          *reinterpret_cast<double2*>(E1 + r * LDE + c2) = __ldcg(reinterpret_cast<const double2*>(W + r * TB + c2));
+        }
+      }
+      consumerBar();
+      double x[3][6][2];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) x[i][j][0] = x[i][j][1] = 0.0;
+      const double* as = E0 + (rbase + g) * LDE + t;
+      const double* bs = E1 + (cbase + g) * LDE + t;
+#pragma unroll 2
+      for (int kk = 0; kk < TB; kk += 4) {
+        double af[3], bf[6];
+#pragma unroll
+        for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
+#pragma unroll
+        for (int j = 0; j < 6; j++) bf[j] = bs[j * 8 * LDE + kk];
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (kk < cbase + 8 * j + 8) {  // W is lower triangular: column tile j only sees k < its last column + 1
+#pragma unroll
+            for (int i = 0; i < 3; i++) dmma(x[i][j][0], x[i][j][1], af[i], bf[j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const int64_t gr = (int64_t)rowA0 + r;
+          if (gr < p.rows && cc < nc)
+            *reinterpret_cast<double2*>(A + gr * ld + c * TB + cc) = make_double2(x[i][j][0], x[i][j][1]);
+        }
+      __threadfence();
+      fenceProxyAsync();
+      consumerBar();
+      if (tid == 0) stRelease(p.done + (int64_t)bi * p.nbc + c, p.epoch);
+      __syncthreads();  // (B)
+      cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
+      continue;
+    }
+
+    // ---- diagonal job of block d = bi: tiles T1 = (d, d-1) (warps wn = 0) and T2 = (d, d) (warps wn = 1)
+    const int d = bi;
+    const int nd = min(TB, p.n - d * TB);  // valid rows / columns of the diagonal block
+    const int rbase = 24 * wm;
+    if (c >= 0) {
+      if (wn == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
+            double2 a = make_double2(0.0, 0.0);
+            if (rowA0 + r < p.rows) a = *reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc);
+            *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
+          }
+      }
+      if (tid == 0 && !aborted) waitFlag(p.wdone + c, p.epoch, p.abortFlag);
+      consumerBar();
+      LC_STAMP(2)
+      {
+        const double* __restrict__ W = p.wbuf + (int64_t)c * TB * TB;
+        for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
+          const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
+          *reinterpret_cast<double2*>(E1 + r * LDE + c2) = __ldcg(reinterpret_cast<const double2*>(W + r * TB + c2));
+        }
+      }
+      consumerBar();
+      LC_STAMP(3)
+      if (wn == 0) {  // X = M W^T, 24 x 96 per warp, into the registers that held acc1
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 12; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double* as = E0 + (rbase + g) * LDE + t;
+        const double* bs = E1 + g * LDE + t;
+#pragma unroll 1
+        for (int kk = 0; kk < TB; kk += 4) {
+          double af[3], bf[12];
+#pragma unroll
+          for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
+#pragma unroll
+          for (int j = 0; j < 12; j++) bf[j] = bs[j * 8 * LDE + kk];
+#pragma unroll
+          for (int j = 0; j < 12; j++)
+            if (kk < 8 * j + 8) {
+#pragma unroll
+              for (int i = 0; i < 3; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+      }
+      consumerBar();  // every read of M is done: E0 becomes L1 = L(d, d-1)
+      LC_STAMP(4)
+      if (wn == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
+            const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(E0 + r * LDE + cc) = v;
+            if (rowA0 + r < p.rows) *reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc) = v;
+          }
+        __threadfence();
+        fenceProxyAsync();
+      }
+      consumerBar();
+      if (tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+      LC_STAMP(5)
+      if (wn == 1) {  // acc2 += L1 L1^T on the lower triangle of the tile
+        const double* as = E0 + (rbase + g) * LDE + t;
+        const double* bs = E0 + g * LDE + t;
+#pragma unroll 1
+        for (int kk = 0; kk < TB; kk += 4) {
+          double af[3], bf[12];
+#pragma unroll
+          for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
+#pragma unroll
+          for (int j = 0; j < 12; j++) bf[j] = bs[j * 8 * LDE + kk];
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 12; j++)
+              if (8 * j <= rbase + 8 * i + 7) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+    }
+    // D = A(d,d) - acc2 -> S (= E1 region as [96][LDQ]); the W^T operand in E1 is dead (all warps passed the barrier
+    // after the X product); zero outside the valid lower triangle
+    double* S = E1;
+    consumerBar();
+    LC_STAMP(6)
+    for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
+    consumerBar();
+    if (wn == 1) {
+      // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along the
+      // factorization as the extra rows of a trapezoid: they come out as M L^-T
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t + e;
+            if (cc <= r && cc < nd && rowA0 + r < p.rows)
+              S[r * LDQ + cc] = A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] - acc[i][j][e];
+          }
+    }
+    consumerBar();
+    LC_STAMP(7)
+    potrfTile(S, nd, colbuf, ybuf, warp, lane);
+    LC_STAMP(8)
+    if (nd < TB) {
+      // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion
+      for (int r = nd + warp; r < TB; r += 8)
+        if (rowA0 + r < p.rows) {
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            const int cc = lane + 32 * u;
+            if (cc < nd) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
+          }
+        }
+      consumerBar();
+      for (int idx = tid; idx < (TB - nd) * TB; idx += kConsumers) {
+        const int r = nd + idx / TB, cc = idx % TB;
+        S[r * LDQ + cc] = (r == cc) ? 1.0 : 0.0;
+      }
+      for (int idx = tid; idx < nd * (TB - nd); idx += kConsumers) S[(idx / (TB - nd)) * LDQ + nd + idx % (TB - nd)] = 0.0;
+      consumerBar();
+    }
+    if (d + 1 < p.nbr) {  // somebody below needs W_d = L(d,d)^-1: first, it is on the critical path
+      invertTile(S, E0, reinterpret_cast<double*>(smem + kSmemT), tid, warp, lane);
+      LC_STAMP(9)
+      double* __restrict__ W = p.wbuf + (int64_t)d * TB * TB;
+      for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
+        const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
+        *reinterpret_cast<double2*>(W + r * TB + c2) = *reinterpret_cast<const double2*>(E0 + r * LDE + c2);
+      }
+      __threadfence();
+      consumerBar();
+      if (tid == 0) stRelease(p.wdone + d, p.epoch);
+      LC_STAMP(10)
+    }
+    // L(d,d) -> global (lower triangle, coalesced rows)
+    for (int r = warp; r < nd; r += 8)
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int cc = lane + 32 * u;
+        if (cc <= r) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
+      }
+    fenceProxyAsync();
+    __syncthreads();  // (B)
+    LC_STAMP(11)
+    cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
+  }
+#undef LC_STAMP
+  if (p.dbg && tid == 0) {
+    long long* q = p.dbg + 64 * 16 + (int64_t)blockIdx.x * 4;
+    q[0] = cycMain, q[1] = cycEpi, q[2] = 0, q[3] = nJobs;
+  }
+  if (tid == 0 && *(volatile unsigned*)p.abortFlag == p.epoch) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    A[0] = nan;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encodeTiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// flags, ticket, abort word and block inverses of the launches issued on one stream of one device. Launches on a stream
+// run in order and every launch leaves the state consistent (fresh epoch, ticket base advanced), so a stream's launches
+// share it; different streams (the lanes of concurrent lumps, other Solvers) get their own.
+struct LcState {
+  DevBuf<long long> dbg;
+  DevBuf<unsigned> words;
+  DevBuf<double> wbuf;
+  int nbcCap = 0;
+  int64_t tileCap = 0;
+  unsigned epoch = 0, ticketBase = 0;
+};
+long long*& lastDbg() {
+  static long long* p = nullptr;
+  return p;
+}
+std::mutex& lcMutex() {
+  static std::mutex m;
+  return m;
+}
+LcState& lcState(cudaStream_t st) {
+  static std::map<std::pair<int, cudaStream_t>, LcState> states;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(lcMutex());
+  return states[{dev, st}];
+}
+
+}  // namespace
+
+// read at every call (a getenv per wide lump is noise): tests and probes flip the switches at run time
+// diagnostics: the stamps of the last instrumented launch (synchronizes); returns the bytes copied
+int64_t lumpCholDebugRead(void* out, int64_t bytes) {
+  if (!lastDbg()) return 0;
+  const int64_t n = std::min<int64_t>(bytes, (64 * 16 + 1024 * 4) * (int64_t)sizeof(long long));
+  B200_CUDA(cudaDeviceSynchronize());
+  B200_CUDA(cudaMemcpy(out, lastDbg(), n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int lumpCholMinWidth() {
+  const char* e = getenv("BSPB200_LUMPCHOL_MIN");
+  return e ? atoi(e) : 384;
+}
+
+// Cholesky of the (n + rowsBelow) x n trapezoid by the tile-DAG kernel; false when the shape / alignment is not eligible
+// (the caller then runs the recursive schedule)
+bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int64_t ld) {
+  const char* sw = getenv("BSPB200_LUMPCHOL");
+  if ((sw && atoi(sw) == 0) || n < lumpCholMinWidth() || n > (1 << 20) || n + rowsBelow > (1 << 24)) return false;
+  if (ld % 2 != 0 || n % 2 != 0 || ((uintptr_t)A & 15) != 0 || !encodeTiled()) return false;  // TMA: 16-byte rows / base
+  LcParams p;
+  p.A = A, p.ld = ld, p.n = (int)n, p.rows = (int)(n + rowsBelow);
+  p.nbc = ceilDiv(n, TB), p.nbr = ceilDiv(n + rowsBelow, TB);
+  int64_t jobs = 1;
+  for (int c = 0; c < p.nbc; c++) jobs += p.nbr - c - 1;
+  p.numJobs = (int)jobs;
+
+  LcState& s = lcState(st);
+  const int64_t tiles = (int64_t)p.nbr * p.nbc;
+  if (p.nbc > s.nbcCap || tiles > s.tileCap) {
+    B200_CUDA(cudaStreamSynchronize(st));
+    s.nbcCap = std::max(p.nbc, s.nbcCap * 2);
+    s.tileCap = std::max(tiles, s.tileCap * 2);
+    s.words.resize((size_t)(2 + s.nbcCap + s.tileCap));
+    s.wbuf.resize((size_t)s.nbcCap * TB * TB);
+    B200_CUDA(cudaMemsetAsync(s.words.ptr(), 0, s.words.size() * sizeof(unsigned), st));
+    s.epoch = 0, s.ticketBase = 0;
+  }
+  p.ticket = s.words.ptr(), p.abortFlag = s.words.ptr() + 1, p.wdone = s.words.ptr() + 2;
+  p.done = s.words.ptr() + 2 + s.nbcCap;
+  p.wbuf = s.wbuf.ptr();
+  p.epoch = ++s.epoch, p.ticketBase = s.ticketBase;
+  p.dbg = nullptr;
+  if (const char* e = getenv("BSPB200_LUMPCHOL_DBG")) {
+    if (atoi(e) != 0) {
+      if (s.dbg.size() == 0) s.dbg.resize(64 * 16 + 1024 * 4);
+      B200_CUDA(cudaMemsetAsync(s.dbg.ptr(), 0, s.dbg.size() * sizeof(long long), st));
+      p.dbg = s.dbg.ptr();
+      lastDbg() = s.dbg.ptr();
+    }
+  }
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)(n + rowsBelow)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {BK, TB}, estr[2] = {1, 1};
+  const CUresult r = encodeTiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, A, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+
+  int dev = 0, sms = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = (int)std::min<int64_t>(sms, jobs);
+  ensureDynSmem((const void*)lump_chol_kernel, kSmemBytes);
+  ProfScope prof(st, KC_LUMP_CHOL, (double)n * n * n / 3 + (double)rowsBelow * n * n, 0);
+  lump_chol_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
+  B200_LAUNCH_CHECK();
+  s.ticketBase += (unsigned)(jobs + grid);
+  return true;
+}
+
+}  // namespace b200
+}  // namespace BaSpaCho

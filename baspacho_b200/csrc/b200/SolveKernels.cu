@@ -248,13 +248,7 @@ void trsvBlock(cudaStream_t st, int batch, int n, Operand<T> L, int64_t ldl, Ope
                bool transposed) {
   if (n > kTB) throw std::runtime_error("trsvBlock: block too large");
   auto smemFor = [](int) { return ((size_t)kTB * kTLD + kTB) * sizeof(T); };
-  static bool once = [&] {
-    size_t mx = smemFor(maxBlockDim<T>());
-    if (mx > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
-    return true;
-  }();
-  (void)once;
+  ensureDynSmem((const void*)trsv_block_kernel<T>, smemFor(maxBlockDim<T>()));
   ProfScope prof(st, KC_SOLVE_DENSE, (double)n * n * nRHS * batch, (double)n * (n + 1) / 2 * sizeof(T) * batch);
   trsv_block_kernel<T><<<dim3(1, 1, batch), kTrsvWarps * 32, smemFor(n), st>>>(n, L, ldl, C, ldc, nRHS, transposed);
   B200_LAUNCH_CHECK();
@@ -944,11 +938,7 @@ void invertBlockList(cudaStream_t st, int batch, const InvBlockDesc* list, int64
                      Operand<T> invScratch) {
   if (count <= 0) return;
   const size_t ismem = ((size_t)2 * kTB * kTLD + kTB) * sizeof(T);
-  static bool once = [&] {
-    B200_CUDA(cudaFuncSetAttribute(invert_blocks_list_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-    return true;
-  }();
-  (void)once;
+  ensureDynSmem((const void*)invert_blocks_list_kernel<T>, ismem);
   ProfScope prof(st, KC_SOLVE_DENSE, 0, (double)count * kTB * kTB / 2 * sizeof(T) * batch);
   invert_blocks_list_kernel<T><<<dim3((unsigned)count, 1, batch), 128, ismem, st>>>(list, data, invScratch);
   B200_LAUNCH_CHECK();
@@ -961,11 +951,7 @@ static void launchChain(cudaStream_t st, int batch, int64_t n, Operand<T> L, int
   const int nbk = ceilDiv(n, kTB);
   const int perItem = nbk + (TR ? 0 : ceilDiv(rowsBelow, kTB));
   const size_t smem = ((size_t)kTB * kTB + (size_t)NR * kTB + (TR ? (size_t)kChWarps * NR * kTB : 0)) * sizeof(T);
-  static bool once = [&] {
-    B200_CUDA(cudaFuncSetAttribute(trsv_chain_kernel<T, TR, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return true;
-  }();
-  (void)once;
+  ensureDynSmem((const void*)trsv_chain_kernel<T, TR, NR>, smem);
   trsv_chain_kernel<T, TR, NR><<<dim3((unsigned)perItem * batch, 1, 1), kChThreads, smem, st>>>(
       n, nbk, L, ldl, C, ldc, nRHS, W, cs->flags, cs->flagsPerItem, cs->ticket, cs->ticketBase, cs->epoch + 1,
       TR ? 0 : rowsBelow, rowMap, vec);
@@ -988,22 +974,14 @@ bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
     return false;
   }
   const size_t smem = ((size_t)kTB * kTLD + kTB + (size_t)kTrsvWarps * kTB) * sizeof(T);
-  static bool once = [&] {
-    B200_CUDA(cudaFuncSetAttribute(solve_step_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA(cudaFuncSetAttribute(solve_step_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return true;
-  }();
-  (void)once;
+  ensureDynSmem((const void*)solve_step_kernel<T, false>, smem);
+  ensureDynSmem((const void*)solve_step_kernel<T, true>, smem);
   const int64_t ldx = n;
   // inverse-based diagonal steps when the caller provided room for the block inverses (2 x 96 x 96 per block)
   const bool useInv = invScratch.base != nullptr;
   if (useInv && !inversesReady) {
     const size_t ismem = ((size_t)2 * kTB * kTLD + kTB) * sizeof(T);
-    static bool onceInv = [&] {
-      B200_CUDA(cudaFuncSetAttribute(invert_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-      return true;
-    }();
-    (void)onceInv;
+    ensureDynSmem((const void*)invert_blocks_kernel<T>, ismem);
     ProfScope prof(st, KC_SOLVE_DENSE, 0, (double)n * kTB / 2 * sizeof(T) * batch);
     invert_blocks_kernel<T><<<dim3(ceilDiv(n, nb), 1, batch), 128, ismem, st>>>(n, L, ldl, invScratch);
     B200_LAUNCH_CHECK();

@@ -596,12 +596,8 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // stress 3.4 ms, and was removed: profiles/README.md.)
   static const int mode = getenv("BSPB200_GATHER") ? atoi(getenv("BSPB200_GATHER")) : 1;
   auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
-    static bool once = [&] {
-      B200_CUDA(cudaFuncSetAttribute(light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      B200_CUDA(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      return true;
-    }();
-    (void)once;
+    ensureDynSmem((const void*)light, smem);
+    ensureDynSmem((const void*)heavy, smem);
     constexpr int NT = kStagedWarps * 32;
     if (plan.numLight > 0) {
       if (mode == 2)

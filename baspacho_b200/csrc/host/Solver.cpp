@@ -480,7 +480,7 @@ SolverPtr createSolver(const Settings& settings, const vector<int64_t>& paramSiz
   for (int64_t i = givenElimEnd; i < nParams; i++) sortedBottomSizes[invPerm[i - givenElimEnd]] = paramSize[i];
 
   const ComputationModel* model = settings.computationModel ? settings.computationModel
-                                  : settings.backend == BackendCuda ? &ComputationModel::model_Cuda117_2080Ti
+                                  : settings.backend == BackendCuda ? &ComputationModel::model_B200  // this library's device
                                                                     : &ComputationModel::model_OpenBlas_i7_1185g7;
 
   EliminationTree et(sortedBottomSizes, sortedBottom, model);

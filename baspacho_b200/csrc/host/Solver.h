@@ -117,7 +117,9 @@ struct ComputationModel;
 struct Settings {
   bool findSparseEliminationRanges = true;
   int numThreads = 16;
-  BackendType backend = BackendFast;
+  // the reference defaults to BackendFast (Solver.h:203); this library has no CPU numeric path, so a default-constructed
+  // Settings - `createSolver({}, ...)`, the common call of the reference's examples - selects the device backend
+  BackendType backend = BackendCuda;
   AddFillPolicy addFillPolicy = AddFillComplete;
   const ComputationModel* computationModel = nullptr;
 };

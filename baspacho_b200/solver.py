@@ -136,5 +136,23 @@ class Solver(_capi.SolverHandle):
             vptr = hp(vec)
         self.factor_solve_host_ptr(dt, hp(data), hp(factor_out) if factor_out is not None else 0, vptr, ld, n_rhs)
 
+    def host_copy_bytes(self):
+        """(h2d, d2h) bytes moved by the last factor_solve_host / factor_solve_host_batched call"""
+        a, b = _capi.c_i64(), _capi.c_i64()
+        self.api.check(self.api.host_copy_bytes(self._h, _capi.C.byref(a), _capi.C.byref(b)))
+        return a.value, b.value
+
+    def factor_solve_host_batched(self, datas, vecs):
+        """datas: (batch, dataSize), vecs: (batch, n_rhs, ld) HOST buffers (numpy or pinned torch CPU tensors)"""
+        def hp(a):
+            return a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+        batch = len(datas)
+        dt = _capi.dtype_code(datas[0].dtype) if isinstance(datas[0], np.ndarray) else self._dt(datas[0])
+        shape = tuple(vecs[0].shape)
+        n_rhs, ld = (1, shape[0]) if len(shape) == 1 else shape
+        dp = (_capi.vp * batch)(*[hp(datas[q]) for q in range(batch)])
+        vpz = (_capi.vp * batch)(*[hp(vecs[q]) for q in range(batch)])
+        self.api.check(self.api.factor_solve_host_batched(self._h, dt, dp, batch, vpz, ld, n_rhs))
+
     def launch_count(self):
         return int(self.api.launch_count())

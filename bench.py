@@ -146,14 +146,31 @@ def gen_problem(api, wl):
     return sizes, ptrs, inds, ranges, w
 
 
-def canonical_work(wl, model):
-    """algorithmic flops of the workload on the skeleton the B200 arm builds (both arms report against it)"""
-    import baspacho_b200 as bsp
-    sizes, ptrs, inds, ranges, w = gen_problem(bsp.api(), wl)
-    s = bsp.Solver.create(sizes, ptrs, inds, ranges, backend=bsp.BACKEND_SYMBOLIC_ONLY, computation_model=model,
-                          find_sparse_elim_ranges=w["auto"])
-    we = s.work_estimate()
-    return we, s
+def algorithmic_work(solver_cls, api, backend_symbolic, wl, model):
+    """Algorithmic flops of the workload (from the skeleton alone, the excess an implementation chooses to
+    execute does not count): the smaller of the flop counts of (a) the skeleton the B200 arm factors (`model`) and (b) the
+    skeleton the reference's own default builds (BackendFast -> model_OpenBlas_i7, Solver.cpp:679-683: the least
+    supernode merging of the presets). On the BAL-shaped and FLAT problems the two agree to < 1 %; on GRID 120^2 the
+    B200 preset merges far more (198.7 GF executed) than necessary (65.6 GF) - GF/s is quoted on the necessary work.
+    `solver_cls` / `api` / `backend_symbolic`: the library that counts (product for the b200 arm, oracle for the CPU arm)."""
+    sizes, ptrs, inds, ranges, w = gen_problem(api, wl)
+    out = {}
+    for name, m in (("executed", model), ("reference_default", 0)):
+        s = solver_cls.create(sizes, ptrs, inds, ranges, backend=backend_symbolic, computation_model=m,
+                              find_sparse_elim_ranges=w["auto"])
+        out[name] = s.work_estimate()
+        out[name]["lumps"] = s.num_lumps
+        out[name]["order"] = s.order
+    best = min(("executed", "reference_default"), key=lambda k: out[k]["factor_flops"] + out[k]["solve_flops_per_rhs"])
+    out["algorithmic"] = out[best]
+    return out
+
+
+def make_config(w, work, batch):
+    """the `config` object, identical (keys and values) in every arm of the same workload"""
+    a = work["algorithmic"]
+    return {"workload": w["desc"], "batch": batch, "n_rhs": 1, "order": a["order"],
+            "algorithmic_gflop": round((a["factor_flops"] + a["solve_flops_per_rhs"]) / 1e9, 3)}
 
 
 def dist_setup(n_gpus):
@@ -163,15 +180,15 @@ def dist_setup(n_gpus):
 
 
 def run_reference(args):
-    """the reference's CPU path (restated BLAS backend, all host threads) on the same workload"""
+    """the reference's CPU path (restated BLAS backend, all host threads) on the same workload; loads oracle/ only"""
     rank, world, _ = dist_setup(args.gpus)
     if rank != 0:
         return
-    from baspacho_b200 import _capi
     from oracle import cpu as ocpu
+    from baspacho_b200 import _capi  # constants + ctypes binding class only: the product library is NOT loaded
     api = ocpu.api()
     cores = os.cpu_count()
-    we, _ = canonical_work(args.workload, args.model)
+    work = algorithmic_work(ocpu.OracleSolver, api, _capi.BACKEND_SYMBOLIC_ONLY, args.workload, args.model)
     sizes, ptrs, inds, ranges, w = gen_problem(api, args.workload)
     t0 = time.time()
     s = ocpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=cores,
@@ -180,7 +197,8 @@ def run_reference(args):
     data0 = api.random_data_array(s.data_size, -1, 1, 37)
     s.damp(data0, 0.0, s.order * 1.2)
     rhs0 = api.random_data_array(s.order, -1, 1, 38).reshape(1, s.order)
-    flops = we["factor_flops"] + we["solve_flops_per_rhs"]
+    a = work["algorithmic"]
+    flops = a["factor_flops"] + a["solve_flops_per_rhs"]
     times = []
     for it in range(args.warmup + args.steps):
         data, x = data0.copy(), rhs0.copy()
@@ -192,13 +210,15 @@ def run_reference(args):
             times.append(dt)
     tot = sum(times)
     value = args.steps * flops / tot / 1e9
+    batch = w.get("batch", 0) or world
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "order": s.order, "analysis_s": round(analysis_s, 3)},
+        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if w.get("batch") else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(w, work, batch),
+        "detail": {"analysis_s": round(analysis_s, 3), "lumps": s.num_lumps, "one_matrix_per_step": True},
         "cpu_baseline": {"value": value, "unit": "GF/s", "cores": cores, "kind": "port",
-                         "sample": "full workload (1 factor+solve per step), restated reference BackendFast: OpenBLAS "
+                         "sample": "one matrix of the workload per step (1 factor+solve), restated reference BackendFast: OpenBLAS "
                                    f"{os.path.basename(ocpu.blas_path() or 'none')} + {cores} threads"},
         "e2e": {"value": value, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -224,25 +244,26 @@ def measure_dgemm_peak(torch, dev):
     return best
 
 
-def run_b200(args):
+def measure_workload(args, wl, steps, warmup, rank, world, dev, sampler=None, with_profile=False, with_unfused=False):
+    """times `steps` steps of one workload on this rank's GPU (CUDA events on the solver's stream, max over ranks) and its
+    end-to-end form through the host-buffer C-ABI calls; returns a dict (identical on every rank up to rank-local keys)"""
     import torch
     import baspacho_b200 as bsp
-    rank, world, local = dist_setup(args.gpus)
-    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    dist = torch.distributed if world > 1 else None
     api = bsp.api()
-    sizes, ptrs, inds, ranges, w = gen_problem(api, args.workload)
+    sizes, ptrs, inds, ranges, w = gen_problem(api, wl)
     t0 = time.time()
     s = bsp.Solver.create(sizes, ptrs, inds, ranges, computation_model=args.model, find_sparse_elim_ranges=w["auto"])
     analysis_s = time.time() - t0
     stream = torch.cuda.Stream(device=dev)
     s.set_stream(stream)
-    we = s.work_estimate()
-    flops = we["factor_flops"] + we["solve_flops_per_rhs"]
+    work = algorithmic_work(bsp.Solver, api, bsp.BACKEND_SYMBOLIC_ONLY, wl, args.model) if rank == 0 else None
+    if world > 1:
+        box = [work]
+        dist.broadcast_object_list(box, src=0)
+        work = box[0]
+    a = work["algorithmic"]
+    flops = a["factor_flops"] + a["solve_flops_per_rhs"]
     batch_total = w.get("batch", 0)
     if batch_total:
         # config 4: a fixed batch of identically structured matrices, contiguous shard per rank (strong scaling)
@@ -253,34 +274,32 @@ def run_b200(args):
         for q in range(n_items):
             s.damp(data_h[q], 0.0, s.order * 1.3)
         rhs_h = np.stack([api.random_data_array(s.order, -1, 1, 1038 + q).reshape(1, s.order) for q in range(lo, hi)]) if n_items else np.zeros((0, 1, s.order))
-        flops_rank = flops * n_items
     else:
         # every rank owns one matrix of the batch: same structure, different values (weak scaling)
         n_items = 1
         data_h = api.random_data_array(s.data_size, -1, 1, 37 + rank)
         s.damp(data_h, 0.0, s.order * 1.2)
         rhs_h = api.random_data_array(s.order, -1, 1, 38 + rank).reshape(1, s.order)
-        flops_rank = flops
     pin_data = torch.from_numpy(data_h).pin_memory()
     pin_rhs = torch.from_numpy(rhs_h.copy()).pin_memory()
     pristine = pin_data.to(dev)
-    work = torch.empty_like(pristine)
+    work_d = torch.empty_like(pristine)
     rhs_d = pin_rhs.to(dev)
     x_d = torch.empty_like(rhs_d)
 
     def do_factor():
         if batch_total:
             if n_items:
-                s.factor_batched(work)
+                s.factor_batched(work_d)
         else:
-            s.factor(work)
+            s.factor(work_d)
 
     def do_solve():
         if batch_total:
             if n_items:
-                s.solve_batched(work, x_d)
+                s.solve_batched(work_d, x_d)
         else:
-            s.solve(work, x_d)
+            s.solve(work_d, x_d)
 
     def barrier():
         if world > 1:
@@ -289,7 +308,7 @@ def run_b200(args):
 
     def step():
         with torch.cuda.stream(stream):
-            work.copy_(pristine, non_blocking=True)
+            work_d.copy_(pristine, non_blocking=True)
             x_d.copy_(rhs_d, non_blocking=True)
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(stream)
@@ -299,23 +318,20 @@ def run_b200(args):
             e2.record(stream)
         return e0, e1, e2
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # before the warm-up, so that it is already sampling when the timed region opens
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
-    if rank == 0:
+    if sampler is not None:
         sampler.mark()
     n0 = s.launch_count()
     t_wall = time.perf_counter()
-    evs = [step() for _ in range(args.steps)]
+    evs = [step() for _ in range(steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = s.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
-    fac_ms = [a.elapsed_time(b) for a, b, _ in evs]
-    sol_ms = [b.elapsed_time(c) for _, b, c in evs]
+    clocks = sampler.stop() if sampler is not None else None
+    fac_ms = [a_.elapsed_time(b_) for a_, b_, _ in evs]
+    sol_ms = [b_.elapsed_time(c_) for _, b_, c_ in evs]
     tot_s = (sum(fac_ms) + sum(sol_ms)) * 1e-3
     t = torch.tensor([tot_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -331,65 +347,198 @@ def run_b200(args):
             s.add_mv_from(p0, 0, x0, y)
         torch.cuda.synchronize()
         resid = float((y - r0).norm() / r0.norm())
+    x_head = (x_d[0, 0, :4] if batch_total else x_d[0, :4]).cpu().numpy().tolist() if n_items else None
+    x_gpu = x_d.cpu().numpy() if (rank == 0 and not batch_total) else None
+
+    # ---- the fine-grained op sequence (what INTEGRATION.md's one-line getBackend change delivers without the fused hooks)
+    unfused_ms = None
+    if with_unfused:
+        s.set_fused(False)
+        ts = []
+        for it in range(4):
+            e0, _, e2 = step()
+            torch.cuda.synchronize()
+            if it >= 1:
+                ts.append(e0.elapsed_time(e2))
+        s.set_fused(True)
+        unfused_ms = float(np.mean(ts))
 
     # ---- e2e: the C-ABI host-buffer call (pinned host memory in, solution out), H2D + D2H inside the timed region
     x_host = torch.empty_like(pin_rhs).pin_memory()
     e2e_times = []
-    for it in range(2 + max(3, args.steps // 2)):
+    h2d = d2h = 0
+    for it in range(2 + max(3, steps // 2)):
         x_host.copy_(pin_rhs)
         barrier()
         t0 = time.perf_counter()
         if batch_total:
-            for q in range(n_items):  # the host-buffer entry point takes one matrix at a time
-                s.factor_solve_host(pin_data[q], x_host[q], None)
+            if n_items:
+                s.factor_solve_host_batched(pin_data, x_host)
         else:
             s.factor_solve_host(pin_data, x_host, None)
         dt = time.perf_counter() - t0
         if it >= 2:
             e2e_times.append(dt)
+    if n_items:
+        h2d, d2h = s.host_copy_bytes()
+    e2e_resid = None
+    if n_items and not batch_total:  # the end-to-end call's own answer: residual of its solution
+        xe = x_host.to(dev)
+        y = torch.zeros_like(rhs_d)
+        with torch.cuda.stream(stream):
+            s.add_mv_from(pristine, 0, xe, y)
+        torch.cuda.synchronize()
+        e2e_resid = float((y - rhs_d).norm() / rhs_d.norm())
     te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
     e2e_s = float(te.item())
 
+    prof = None
+    if with_profile and rank == 0:
+        # per-kernel-class profile of one more step (events around every launch of our kernels)
+        api.profile(True)
+        step()
+        torch.cuda.synchronize()
+        prof = api.profile_json()
+        api.profile(False)
+
+    total_flops = flops * batch_total if batch_total else world * flops
+    ex = work["executed"]
+    res = {
+        "w": w, "work": work, "solver": s, "problem": (sizes, ptrs, inds, ranges), "rhs_h": rhs_h, "x_gpu": x_gpu,
+        "batch": batch_total or world, "n_items": n_items, "steps": steps, "warmup": warmup,
+        "value": steps * total_flops / tot_max / 1e9, "ms_per_step": tot_max / steps * 1e3,
+        "factor_ms": float(np.mean(fac_ms)), "solve_ms": float(np.mean(sol_ms)),
+        "factor_gfs": a["factor_flops"] * (n_items if batch_total else 1) / (np.mean(fac_ms) * 1e-3) / 1e9,
+        "residual": resid, "wall_s_timed_region": t_wall, "x_head": x_head, "launches": launches, "clocks": clocks,
+        "unfused_ms_per_step": unfused_ms, "kernel_classes": prof, "analysis_s": round(analysis_s, 3),
+        "e2e": {"value": total_flops / e2e_s / 1e9, "unit": "GF/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()),
+                "bytes_note": "summed over ranks; counted by the library from the copies it issues (upper triangles of wide "
+                              "diagonal blocks are not uploaded)",
+                "residual": e2e_resid,
+                "api": "bspb200_factor_solve_host_batched" if batch_total else "bspb200_factor_solve_host (C ABI, pinned host "
+                       "buffers; point columns uploaded in chunks, the elimination of a chunk overlaps the next upload)"},
+        "detail": {"order": s.order, "data_size": s.data_size, "lumps": s.num_lumps, "items_on_rank0": n_items,
+                   "executed_gflop": round((ex["factor_flops"] + ex["solve_flops_per_rhs"]) / 1e9, 3),
+                   "algorithmic_factor_gflop": round(a["factor_flops"] / 1e9, 3), "nnz_l": ex["nnz_l"],
+                   "dense_lump_sizes": np.diff(s.lumpStart[w["n_elim"]:]).tolist()[-8:] if w["n_elim"] else None,
+                   "l2_policy": "inputs larger than L2; the in-place factor is restored from a pristine device copy between steps",
+                   "timing": "cuda events per step on the solver stream; sum over steps; max over ranks",
+                   "analysis_s": round(analysis_s, 3)},
+    }
+    return res
+
+
+def ref_cuda_leg(args, wl, steps=3, warmup=2):
+    """the reference's CUDA algorithm restated on cuSOLVER / cuBLAS (oracle/RefCudaOps.cu) on the same GPU, same inputs: on
+    the B200 arm's skeleton (same supernodes) and on its own preset's (model_Cuda117_2080Ti, what the reference picks)"""
+    import torch
+    from oracle import refcuda
+    api = refcuda.api()
+    sizes, ptrs, inds, ranges, w = gen_problem(api, wl)
+    out = {}
+    for name, model in (("same_skeleton", args.model), ("own_preset_2080ti", 1)):
+        s = refcuda.RefCudaSolver.create(sizes, ptrs, inds, ranges, computation_model=model, find_sparse_elim_ranges=w["auto"])
+        stream = torch.cuda.Stream()
+        s.set_stream(stream)
+        data_h = api.random_data_array(s.data_size, -1, 1, 37)
+        s.damp(data_h, 0.0, s.order * 1.2)
+        pristine = torch.from_numpy(data_h).cuda()
+        work_d = torch.empty_like(pristine)
+        rhs_d = torch.from_numpy(api.random_data_array(s.order, -1, 1, 38).reshape(1, s.order)).cuda()
+        x_d = torch.empty_like(rhs_d)
+        fac, sol = [], []
+        for it in range(warmup + steps):
+            with torch.cuda.stream(stream):
+                work_d.copy_(pristine, non_blocking=True)
+                x_d.copy_(rhs_d, non_blocking=True)
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record(stream)
+                s.factor(work_d)
+                e1.record(stream)
+                s.solve(work_d, x_d)
+                e2.record(stream)
+            torch.cuda.synchronize()
+            if it >= warmup:
+                fac.append(e0.elapsed_time(e1)), sol.append(e1.elapsed_time(e2))
+        out[name] = {"ms_per_step": float(np.mean(fac) + np.mean(sol)), "factor_ms": float(np.mean(fac)),
+                     "solve_ms": float(np.mean(sol)), "lumps": s.num_lumps, "x_head": x_d[0, :4].cpu().numpy().tolist()}
+        del s, pristine, work_d
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_b200(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()  # before the warm-up, so that it is already sampling when the timed region opens
+    m = measure_workload(args, args.workload, args.steps, args.warmup, rank, world, dev, sampler=sampler,
+                         with_profile=True, with_unfused=(rank == 0 and world == 1))
+    # BASELINE config 4 (batch = 64 identical-structure FLAT-2000, sharded over the GPUs, strong scaling) rides along
+    # with the headline workload so that every N of the driver's scaling run records it
+    c4 = None
+    if args.workload == "bal" and not args.no_config4:
+        c4 = measure_workload(args, "flat_batch", min(args.steps, 5), 3, rank, world, dev)
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            torch.distributed.destroy_process_group()
         return
 
-    # ---- per-kernel-class profile of one more step (events around every launch of our kernels)
-    api.profile(True)
-    step()
-    torch.cuda.synchronize()
-    prof = api.profile_json()
-    api.profile(False)
+    w, work, s = m["w"], m["work"], m["solver"]
+    a = work["algorithmic"]
+    prof = m["kernel_classes"]
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     dgemm_peak = measure_dgemm_peak(torch, dev)
-    g = prof["gemm"]
-    gemm_tf = g["flops"] / max(g["ms"], 1e-9) / 1e9
-    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture (never measured under a profiler
-    # here); per launch, averaged over the captured launches like `achieved` is averaged over the step's launches
+    # dominant kernel: the tensor-bound class with the largest share of the step
+    dom = max(("lump_chol", "gemm"), key=lambda k: prof[k]["ms"])
+    g = prof[dom]
+    dom_tf = g["flops"] / max(g["ms"], 1e-9) / 1e9
+    names = {"gemm": "gemm_nt_f64_kernel (DMMA m8n8k4 SYRK/GEMM tiles of the blocked supernode Cholesky)",
+             "lump_chol": "lump_chol_kernel (persistent left-looking tile Cholesky of a wide supernode: TMA -> smem -> DMMA "
+                          "m8n8k4 tiles, device-side dependency flags; algorithmic flops n^3/3 + rows n^2 of the lump column)"}
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if args.workload == "bal" and os.path.exists(tpath):
-        tj = json.load(open(tpath))["gemm_nt_f64_kernel"]
-        traffic, traffic_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("source", "launches", "largest_launch")}
-    roofline = {"kernel": "gemm_nt_f64_kernel (DMMA m8n8k4 SYRK/GEMM tiles of the blocked supernode Cholesky)",
-                "bound": "tensor", "achieved": gemm_tf, "peak": dgemm_peak, "unit": "TFLOP/s",
-                "frac": gemm_tf / dgemm_peak if dgemm_peak else None, "traffic": traffic, "traffic_note": traffic_note,
+        tj = json.load(open(tpath)).get({"gemm": "gemm_nt_f64_kernel", "lump_chol": "lump_chol_kernel"}[dom])
+        if tj:
+            traffic, traffic_note = tj["dram_bytes_per_launch"], {k: tj[k] for k in ("source", "launches", "largest_launch") if k in tj}
+    # floor of the whole step: dense flops at the DGEMM peak + elimination and solve bytes at the HBM peak (SURVEY 8d)
+    ex = work["executed"]
+    elim_bytes = a["elim_bytes"]
+    solve_bytes = 8.0 * (2.0 * s.data_size + 4.0 * s.order)
+    dense_flops = a["factor_flops"] - a["elim_flops"]
+    floor_ms = (dense_flops / (dgemm_peak * 1e12) + (elim_bytes + solve_bytes) / (hbm_peak * 1e9)) * 1e3 if dgemm_peak else None
+    roofline = {"kernel": names[dom], "bound": "tensor", "achieved": dom_tf, "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": dom_tf / dgemm_peak if dgemm_peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json holds no fp64 figure; "
                                "tcgen05 has no f64 kind, DMMA is the fp64 tensor path)",
-                "launches_per_step": g["launches"], "share_of_step_ms": g["ms"]}
+                "launches_per_step": g["launches"], "share_of_step_ms": g["ms"],
+                "frac_step": floor_ms / m["ms_per_step"] if floor_ms else None,
+                "floor_ms_step": floor_ms,
+                "floor_note": "dense flops / DGEMM peak + (elimination bytes + solve bytes of SURVEY 8d) / HBM peak"}
     eg, ef = prof["elim_gather"], prof["elim_factor"]
     roofline_hbm = None
     if ef["launches"]:
+        ms = ef["ms"] + eg["ms"]
         roofline_hbm = {"kernels": "elim_factor_lumps + elim_gather (sparse elimination)", "bound": "hbm",
-                        "achieved": (ef["bytes"] + eg["bytes"]) / max(ef["ms"] + eg["ms"], 1e-9) / 1e6,
-                        "peak": hbm_peak, "unit": "GB/s",
-                        "frac": (ef["bytes"] + eg["bytes"]) / max(ef["ms"] + eg["ms"], 1e-9) / 1e6 / hbm_peak,
+                        "achieved": elim_bytes / max(ms, 1e-9) / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": elim_bytes / max(ms, 1e-9) / 1e6 / hbm_peak,
+                        "bytes": elim_bytes, "bytes_note": "SURVEY 8d: read+write every eliminated column once, read-modify-write each target entry once",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
-                        "ms": ef["ms"] + eg["ms"]}
+                        "ms": ms}
 
     # ---- CPU baseline (oracle port of the reference's BLAS backend) on a bounded sample: the full workload once
     cpu_baseline = None
@@ -397,112 +546,81 @@ def run_b200(args):
         try:
             from baspacho_b200 import _capi
             from oracle import cpu as ocpu
+            sizes, ptrs, inds, ranges = m["problem"]
             cores = os.cpu_count()
             o = ocpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=cores,
                                          find_sparse_elim_ranges=w["auto"])
             d = ocpu.api().random_data_array(o.data_size, -1, 1, 37)
             o.damp(d, 0.0, o.order * 1.2)
-            xr = (rhs_h[0] if batch_total else rhs_h).copy()
+            xr = (m["rhs_h"][0] if w.get("batch") else m["rhs_h"]).copy()
             t0 = time.perf_counter()
             o.factor(d)
             o.solve(d, xr)
             dt = time.perf_counter() - t0
+            flops = a["factor_flops"] + a["solve_flops_per_rhs"]
             cpu_baseline = {"value": flops / dt / 1e9, "unit": "GF/s", "cores": cores, "kind": "port",
                             "sample": f"full workload, 1 factor+solve ({dt:.2f} s), restated reference BackendFast (OpenBLAS + threads)",
                             # comparable only when both arms built the same skeleton (the CPU arm picks its own
                             # supernode-merge model, as the reference does: Solver.cpp:679-683)
-                            "solution_max_abs_diff_vs_gpu": float(np.abs(xr - x_d.cpu().numpy()).max())
-                            if not batch_total and np.array_equal(o.lumpStart, s.lumpStart)
+                            "solution_max_abs_diff_vs_gpu": float(np.abs(xr - m["x_gpu"]).max())
+                            if m["x_gpu"] is not None and np.array_equal(o.lumpStart, s.lumpStart)
                             and np.array_equal(o.array("permutation"), s.array("permutation")) else None}
         except Exception as e:  # the baseline must never take the GPU number down
             cpu_baseline = {"value": None, "unit": "GF/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
-    total_flops = flops * batch_total if batch_total else world * flops
-    value = args.steps * total_flops / tot_max / 1e9
+    ref_cuda = None
+    if not args.no_ref_cuda and m["n_items"] == 1 and not w.get("batch"):
+        try:
+            ref_cuda = ref_cuda_leg(args, args.workload)
+        except Exception as e:  # noqa: BLE001
+            ref_cuda = {"failed": repr(e)}
+
+    world_desc = f"; batch of {world} such matrices sharded 1 per GPU" if world > 1 and not w.get("batch") else ""
     line = {
-        "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": tot_max / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if batch_total else "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"] + (f"; batch of {world} such matrices sharded 1 per GPU" if world > 1 and not batch_total else ""),
-                   "batch": batch_total or world, "items_on_rank0": n_items,
-                   "order": s.order, "data_size": s.data_size, "nnz_l": we["nnz_l"], "factor_gflop": we["factor_flops"] / 1e9,
-                   "solve_gflop": we["solve_flops_per_rhs"] / 1e9, "n_rhs": 1, "lumps": s.num_lumps,
-                   "dense_lump_sizes": np.diff(s.lumpStart[w["n_elim"]:]).tolist()[-8:] if w["n_elim"] else None,
-                   "l2_policy": "inputs (0.57 GB factor) larger than L2; factor restored from a pristine copy between steps",
-                   "timing": "cuda events per step on the solver stream; sum over steps; max over ranks",
-                   "analysis_s": round(analysis_s, 3)},
-        "factor_ms": float(np.mean(fac_ms)), "solve_ms": float(np.mean(sol_ms)),
-        "factor_gfs": we["factor_flops"] / (np.mean(fac_ms) * 1e-3) / 1e9,
-        "residual": resid, "wall_s_timed_region": t_wall,
-        "x_head": (x_d[0, 0, :4] if batch_total else x_d[0, :4]).cpu().numpy().tolist() if n_items else None,
-        "gpu_launches": launches,
-        "e2e": {"value": total_flops / e2e_s / 1e9, "unit": "GF/s", "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(pin_data.numel() * 8 + pin_rhs.numel() * 8),
-                "d2h_bytes_per_step": int(pin_rhs.numel() * 8),
-                "api": "bspb200_factor_solve_host (C ABI, pinned host buffers)"},
+        "metric": METRIC, "value": m["value"], "unit": "GF/s", "n_gpus": world, "steps": m["steps"], "warmup": m["warmup"],
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w.get("batch") else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(w, work, m["batch"]), "detail": dict(m["detail"], note=world_desc.strip("; ")),
+        "factor_ms": m["factor_ms"], "solve_ms": m["solve_ms"], "factor_gfs": m["factor_gfs"],
+        "residual": m["residual"], "wall_s_timed_region": m["wall_s_timed_region"], "x_head": m["x_head"],
+        "gpu_launches": m["launches"], "e2e": m["e2e"], "unfused_ms_per_step": m["unfused_ms_per_step"],
         "roofline": roofline, "roofline_hbm": roofline_hbm, "kernel_classes": prof,
-        "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "cpu_baseline": cpu_baseline, "ref_cuda": ref_cuda, "clocks": m["clocks"],
     }
+    if c4 is not None:
+        line["config4"] = {"config": make_config(c4["w"], c4["work"], c4["batch"]), "scaling": "strong",
+                           "value": c4["value"], "unit": "GF/s", "ms_per_step": c4["ms_per_step"],
+                           "factor_ms": c4["factor_ms"], "solve_ms": c4["solve_ms"], "items_on_rank0": c4["n_items"],
+                           "steps": c4["steps"], "warmup": c4["warmup"], "residual": c4["residual"],
+                           "gpu_launches": c4["launches"], "e2e": c4["e2e"], "detail": c4["detail"]}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.distributed.destroy_process_group()
 
 
 def run_ref_cuda(args):
-    """second GPU baseline: the REFERENCE's CUDA algorithm - cuSOLVER potrf + cuBLAS trsm/gemm per lump,
-    thread-per-pair elimination with atomics, per-lump synchronous index copies - restated in oracle/RefCudaOps.cu, on the
-    same B200, same skeleton (same supernode-merge preset), same inputs and the same flop count as the b200 arm"""
+    """second GPU baseline as its own arm: see ref_cuda_leg"""
     import torch
     rank, world, local = dist_setup(args.gpus)
     if rank != 0:
         return
     assert torch.cuda.is_available(), "--impl ref_cuda needs a GPU"
-    from oracle import refcuda
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    api = refcuda.api()
-    sizes, ptrs, inds, ranges, w = gen_problem(api, args.workload)
-    t0 = time.time()
-    s = refcuda.RefCudaSolver.create(sizes, ptrs, inds, ranges, computation_model=args.model, find_sparse_elim_ranges=w["auto"])
-    analysis_s = time.time() - t0
-    stream = torch.cuda.Stream(device=dev)
-    s.set_stream(stream)
-    we = s.work_estimate()
-    flops = we["factor_flops"] + we["solve_flops_per_rhs"]
-    data_h = api.random_data_array(s.data_size, -1, 1, 37)
-    s.damp(data_h, 0.0, s.order * 1.2)
-    rhs_h = api.random_data_array(s.order, -1, 1, 38).reshape(1, s.order)
-    pristine = torch.from_numpy(data_h).to(dev)
-    work = torch.empty_like(pristine)
-    rhs_d = torch.from_numpy(rhs_h).to(dev)
-    x_d = torch.empty_like(rhs_d)
-    fac_ms, sol_ms = [], []
-    for it in range(args.warmup + args.steps):
-        with torch.cuda.stream(stream):
-            work.copy_(pristine, non_blocking=True)
-            x_d.copy_(rhs_d, non_blocking=True)
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record(stream)
-            s.factor(work)
-            e1.record(stream)
-            s.solve(work, x_d)
-            e2.record(stream)
-        torch.cuda.synchronize()
-        if it >= args.warmup:
-            fac_ms.append(e0.elapsed_time(e1)), sol_ms.append(e1.elapsed_time(e2))
-    # correctness of what was timed: residual through a dense-free SpMV is not part of this backend; check A x = b with the
-    # product-independent CPU checker's structure-only densify when small, else the solution's finiteness
-    finite = bool(torch.isfinite(x_d).all().item())
-    ms = float(np.mean(fac_ms) + np.mean(sol_ms))
-    line = {"impl": "ref_cuda", "metric": METRIC, "value": flops / (ms * 1e-3) / 1e9, "unit": "GF/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "order": s.order, "lumps": s.num_lumps, "factor_gflop": we["factor_flops"] / 1e9,
-                       "analysis_s": round(analysis_s, 3),
-                       "backend": "restated reference MatOpsCuda.cu: cusolverDnDpotrf + cublasDtrsm/Dgemm per lump, "
-                                  "thread-per-pair elimination with fp64 atomics, per-lump synchronous span-table copy"},
-            "factor_ms": float(np.mean(fac_ms)), "solve_ms": float(np.mean(sol_ms)), "solution_finite": finite,
-            "x_head": x_d[0, :4].cpu().numpy().tolist()}
+    from oracle import refcuda
+    from baspacho_b200 import _capi
+    work = algorithmic_work(refcuda.RefCudaSolver, refcuda.api(), _capi.BACKEND_SYMBOLIC_ONLY, args.workload, args.model)
+    w = WORKLOADS[args.workload]
+    legs = ref_cuda_leg(args, args.workload, steps=args.steps, warmup=args.warmup)
+    a = work["algorithmic"]
+    flops = a["factor_flops"] + a["solve_flops_per_rhs"]
+    best = min(legs.values(), key=lambda r: r["ms_per_step"])
+    line = {"impl": "ref_cuda", "metric": METRIC, "value": flops / (best["ms_per_step"] * 1e-3) / 1e9, "unit": "GF/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": make_config(w, work, 1),
+            "detail": {"backend": "restated reference MatOpsCuda.cu: cusolverDnDpotrf + cublasDtrsm/Dgemm per lump, "
+                                  "thread-per-pair elimination with fp64 atomics, per-lump synchronous span-table copy",
+                       "legs": legs}}
     print(json.dumps(line), flush=True)
 
 
@@ -515,6 +633,8 @@ def main():
     ap.add_argument("--workload", default="bal", choices=sorted(WORKLOADS))
     ap.add_argument("--model", type=int, default=2, help="supernode-merge cost model preset (2 = B200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

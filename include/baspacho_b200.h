@@ -107,10 +107,29 @@ int bspb200_pseudo_factor_from(bspb200_solver* s, int dtype, void* data, int64_t
  * createNumericCtx(0) -> doElimination(internalGetElimCtx(range_index), data, range) */
 int bspb200_do_elimination(bspb200_solver* s, int dtype, void* data, int range_index);
 
+/* Solver::deviceAccessor() (reference Solver.h:48, MatOpsCuda.cu:87-92, Accessor.h:110-200): the trivially copyable
+ * accessor over DEVICE copies of the index arrays, meant to be passed BY VALUE to user kernels that write their blocks
+ * straight into the factor buffer. out_ptrs receives its 8 device pointers in the member order of
+ * PermutedCoalescedAccessor: spanStart, spanToLump, lumpStart, spanOffsetInLump, chainColPtr, chainRowSpan, chainData,
+ * permutation (rebuild the struct with PermutedCoalescedAccessor::init; they stay valid while the solver lives). */
+int bspb200_device_accessor(const bspb200_solver* s, const int64_t** out_ptrs);
+
 /* ---- end-to-end convenience on HOST buffers (pinned or pageable): copies A up, factors, solves n_rhs
- * right-hand sides in place, copies L (if host_factor_out != NULL) and x back. */
+ * right-hand sides in place, copies L (if host_factor_out != NULL) and x back. The strictly-upper triangles of wide
+ * diagonal blocks (a don't-care region of the format) are not uploaded; host_factor_out holds zeros or factor
+ * by-products there. When the first elimination range is large its columns go up in chunks and the elimination of a
+ * chunk overlaps the upload of the next (BSPB200_HOST_CHUNKS, default 12; the chunked summation order is fixed but
+ * differs from factor()'s in the last bits). */
 int bspb200_factor_solve_host(bspb200_solver* s, int dtype, const void* host_data, void* host_factor_out, void* host_vec,
                               int64_t ld, int n_rhs);
+
+/* bytes the last *_host call of this solver moved in each direction (what bench.py declares as e2e traffic) */
+int bspb200_host_copy_bytes(const bspb200_solver* s, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* the batched form (reference Solver::factor / solve on std::vector<T*>, Solver.cpp:459-536) on HOST buffers: `batch`
+ * identically structured matrices and their right-hand sides; uploads of later sub-batches overlap the factorization
+ * of earlier ones; solutions are written back in place */
+int bspb200_factor_solve_host_batched(bspb200_solver* s, int dtype, const void* const* host_datas, int batch,
+                                      void* const* host_vecs, int64_t ld, int n_rhs);
 
 /* ---- dense building blocks on DEVICE pointers (row-major), the kernels behind NumericCtx::potrf / trsm / saveSyrkGemm
  * (reference MatOps.h:124-130); exposed for kernel-level parity tests and roofline measurements.

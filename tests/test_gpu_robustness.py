@@ -1,0 +1,250 @@
+"""GPU tests of the contracts around the hot path (pytest -m gpu): several Solvers at once on their own streams and host
+threads, the device accessor handed by value to a user kernel, the virtual-base-pointer convention of the ...From entry
+points, non-SPD input, and partial factor / solve ranges that cut through sparse-elimination ranges on the fused path."""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+import baspacho_b200 as bsp
+from baspacho_b200 import _capi
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def torch_of(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_two_solvers_on_two_threads_and_streams_match_serial_runs_bitwise():
+    """Two Solvers (different problems, each with wide lumps - panel kernels, tile-DAG Cholesky, chained solves - and
+    small wavefront lumps) factor and solve concurrently from two host threads on two streams, many times; every result
+    must equal the serial result of the same solver bit for bit (the device-side state of the kernels - load counters,
+    flags, tickets, workspaces - is per solver / per stream, reference MatOpsCuda.cu:55-76 keeps handles per context)."""
+    import torch
+    problems = []
+    for seed, (w, h) in ((37, (30, 30)), (41, (34, 26))):
+        sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_GRID, [w, h, 1.0, 2], 6, 6, seed)
+        s = bsp.Solver.create(sizes, ptrs, inds, (), find_sparse_elim_ranges=False, computation_model=_capi.MODEL_B200)
+        assert np.diff(s.lumpStart).max() > 96
+        data = H.make_data(s, seed, np.float64, 1.2)
+        rhs = H.oapi().random_data_array(s.order * 2, -1, 1, seed + 1).reshape(2, s.order)
+        problems.append((s, data, rhs))
+    serial = []
+    for s, data, rhs in problems:
+        d, x = torch_of(data), torch_of(rhs)
+        s.factor(d)
+        s.solve(d, x)
+        torch.cuda.synchronize()
+        serial.append((d.cpu().numpy(), x.cpu().numpy()))
+    errors = []
+
+    def worker(k):
+        try:
+            s, data, rhs = problems[k]
+            st = torch.cuda.Stream()
+            s.set_stream(st)
+            with torch.cuda.stream(st):
+                for rep in range(12):
+                    d, x = torch_of(data), torch_of(rhs)
+                    st.wait_stream(torch.cuda.default_stream())
+                    s.factor(d)
+                    s.solve(d, x)
+                    st.synchronize()
+                    mask = H.flat_lower_mask(s)
+                    if not np.array_equal(d.cpu().numpy()[mask], serial[k][0][mask]) or not np.array_equal(x.cpu().numpy(), serial[k][1]):
+                        errors.append((k, rep))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_device_accessor_passed_by_value_to_a_user_kernel():
+    """Solver::deviceAccessor() (reference Solver.h:48, Accessor.h:110-200): a kernel that is NOT part of the library
+    receives the accessor by value and writes every block of the lower block pattern (and every diagonal block) on the
+    device; the result equals what the host accessor (block_offset, same semantics) places, entry for entry."""
+    import torch
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp"), "libaccessor_kernel.so"])
+    lib = C.CDLL(os.path.join(ROOT, "tests", "cpp", "libaccessor_kernel.so"))
+    lib.accessor_write_blocks.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.accessor_write_blocks.restype = C.c_int
+    lib.accessor_entry_value.argtypes = [C.c_int64] * 4
+    lib.accessor_entry_value.restype = C.c_double
+    sizes, ptrs, inds = H.random_problem(3)
+    s = bsp.Solver.create(sizes, ptrs, inds, (), computation_model=_capi.MODEL_CUDA_2080TI)
+    dev_ptrs = (C.c_void_p * 8)()
+    s.api.check(s.api.device_accessor(s._h, dev_ptrs))
+    assert all(dev_ptrs[i] for i in range(8))
+    rows, cols = [], []
+    for i in range(len(sizes)):  # user block pattern: CSR lower triangle incl. diagonal
+        for j in inds[ptrs[i]:ptrs[i + 1]]:
+            rows.append(i), cols.append(int(j))
+    rb, cb = torch_of(np.array(rows, np.int64)), torch_of(np.array(cols, np.int64))
+    data = torch.zeros(s.data_size, dtype=torch.float64, device="cuda")
+    rc = lib.accessor_write_blocks(dev_ptrs, len(rows), rb.data_ptr(), cb.data_ptr(), data.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    expect = np.zeros(s.data_size)
+    for r, c in zip(rows, cols):
+        off, stride, flipped = s.block_offset(r, c)
+        nr, nc = int(sizes[r]), int(sizes[c])
+        for a in range(nr):
+            for b in range(nc if r != c else a + 1):
+                v = lib.accessor_entry_value(r, c, a, b)
+                if r == c:
+                    expect[off + a * stride + b] = v
+                elif flipped:
+                    expect[off + b * stride + a] = v
+                else:
+                    expect[off + a * stride + b] = v
+    assert np.array_equal(data.cpu().numpy(), expect)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_from_entry_points_honour_virtual_base_pointers(fused):
+    """factorFrom / solveLFrom / solveLtFrom / addMvFrom are called by the reference's examples with pointers BEFORE the
+    start of the real allocation (`matData.data() - spanMatrixOffset(p)`, `vec - spanVectorOffset(p)`,
+    examples/Preconditioner.h:118-135): only data[spanMatrixOffset(p)...] and vec[spanVectorOffset(p)...]
+    may be touched. The sub-buffers here are exactly that large and are surrounded by canaries."""
+    import torch
+    for i in range(3):
+        sizes, ptrs, inds = H.random_problem(i)
+        g = bsp.Solver.create(sizes, ptrs, inds, (), find_sparse_elim_ranges=False, computation_model=_capi.MODEL_CUDA_2080TI)
+        o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, (), backend=_capi.BACKEND_REF, find_sparse_elim_ranges=False,
+                                             computation_model=_capi.MODEL_CUDA_2080TI)
+        g.set_fused(fused)
+        cut = int(g.lumpToSpan[g.num_lumps // 2])
+        m_off, v_off = g.span_matrix_offset(cut), g.span_vector_offset(cut)
+        data = H.make_data(g, 9 + i, np.float64)
+        ref = data.copy()
+        o.factor(ref, 0, cut)          # the state a caller holds after factorUpTo(cut)
+        full = ref.copy()
+        o.factor(full, cut, g.num_spans)
+        canary = 7.25
+        pad = 64
+        sub = torch.full((pad + g.data_size - m_off + pad,), canary, dtype=torch.float64, device="cuda")
+        sub[pad:pad + g.data_size - m_off] = torch_of(ref[m_off:])
+        base = sub.data_ptr() + pad * 8 - m_off * 8  # virtual base: NOT a valid address below m_off
+        g.factor_ptr(_capi.F64, base, cut, -1)
+        torch.cuda.synchronize()
+        got = sub.cpu().numpy()
+        assert (got[:pad] == canary).all() and (got[-pad:] == canary).all()
+        mask = H.flat_lower_mask(g)[m_off:]
+        assert np.abs(got[pad:-pad] - full[m_off:])[mask].max() <= H.TOL_FACTOR * np.abs(full).max()
+        # solveLFrom / solveLtFrom on a vector sub-buffer
+        rhs = H.oapi().random_data_array(g.order, -1, 1, 70 + i).reshape(1, g.order)
+        n_sub = g.order - v_off
+        for mode in (bsp.SOLVE_L, bsp.SOLVE_LT):
+            vsub = torch.full((pad + n_sub + pad,), canary, dtype=torch.float64, device="cuda")
+            vsub[pad:pad + n_sub] = torch_of(rhs[0, v_off:])
+            vbase = vsub.data_ptr() + pad * 8 - v_off * 8
+            g.solve_ptr(_capi.F64, mode, base, vbase, g.order, 1, cut, -1)
+            torch.cuda.synchronize()
+            xr = rhs.copy()
+            o.solve(full, xr, mode, cut, g.num_spans)
+            v = vsub.cpu().numpy()
+            assert (v[:pad] == canary).all() and (v[-pad:] == canary).all()
+            assert np.abs(v[pad:-pad] - xr[0, v_off:]).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max())
+        # addMvFrom on the sub-buffers of the UNFACTORED matrix
+        msub = torch.full((pad + g.data_size - m_off + pad,), canary, dtype=torch.float64, device="cuda")
+        msub[pad:pad + g.data_size - m_off] = torch_of(data[m_off:])
+        xin = torch.full((pad + n_sub + pad,), canary, dtype=torch.float64, device="cuda")
+        xin[pad:pad + n_sub] = torch_of(rhs[0, v_off:])
+        yout = torch.zeros(pad + n_sub + pad, dtype=torch.float64, device="cuda")
+        g.add_mv_from_ptr(_capi.F64, msub.data_ptr() + pad * 8 - m_off * 8, cut, xin.data_ptr() + pad * 8 - v_off * 8, g.order,
+                          yout.data_ptr() + pad * 8 - v_off * 8, g.order, 1, 1.0)
+        torch.cuda.synchronize()
+        A = H.sym_from_lower(g.densify(data)).astype(np.float64)
+        exp = A[v_off:, v_off:] @ rhs[0, v_off:]
+        y = yout.cpu().numpy()
+        assert (y[:pad] == 0).all() and (y[-pad:] == 0).all()
+        assert np.linalg.norm(y[pad:-pad] - exp) / np.linalg.norm(exp) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["wide_lump", "ba_elim", "grid"])
+def test_non_spd_input_gives_non_finite_output_and_never_hangs(kind):
+    """Non-SPD input is silent in the reference (cusolver's info is discarded, MatOpsCuda.cu:523-526) and callers detect
+    it by an isfinite check on the output (examples/Preconditioner.h:178-183). Here: a negative pivot must surface as
+    NaN / Inf in the factor and the solution, and nothing may hang - neither the flag waits of the tile-DAG Cholesky nor
+    those of the chained triangular solves (the test would time out)."""
+    import torch
+    if kind == "wide_lump":
+        sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_FLAT, [200, 1.0], 3, 3, 37)
+        g = bsp.Solver.create(sizes, ptrs, inds, (), find_sparse_elim_ranges=False, computation_model=_capi.MODEL_B200)
+    elif kind == "ba_elim":
+        sizes, ptrs, inds = H.ba_problem(3000, 80, seed=21, window=12)
+        g = bsp.Solver.create(sizes, ptrs, inds, [0, 3000], computation_model=_capi.MODEL_B200)
+    else:
+        sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_GRID, [30, 30, 1.0, 2], 6, 6, 37)
+        g = bsp.Solver.create(sizes, ptrs, inds, (), find_sparse_elim_ranges=False, computation_model=_capi.MODEL_B200)
+    data = H.make_data(g, 5, np.float64, 1.2)
+    bad = data.copy()
+    g.damp(bad, 0.0, -2.4 * g.order)  # diagonal becomes -1.2 * order: negative definite
+    d = torch_of(bad)
+    x = torch_of(H.oapi().random_data_array(g.order, -1, 1, 38).reshape(1, g.order))
+    g.factor(d)
+    g.solve(d, x)
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(d).all())
+    assert not bool(torch.isfinite(x).all())
+    # the solver is still usable afterwards
+    d2 = torch_of(data)
+    x2 = torch_of(H.oapi().random_data_array(g.order, -1, 1, 38).reshape(1, g.order))
+    g.factor(d2)
+    g.solve(d2, x2)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(x2).all())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_partial_ranges_across_sparse_elimination_ranges(fused):
+    """factorUpTo / factorFrom and solveL / solveLt UpTo / From on a bundle-adjustment shaped problem with a GIVEN
+    elimination range plus automatically found ones: cuts at the end of the given range, at the first dense lump, and
+    inside the dense part - the early returns and `continue`s of the fused range drivers (B200Ops.cu fusedFactorRange /
+    fusedSolveL / fusedSolveLt re-implement the reference's range rules, Solver.cpp:164-219, 268-397) against the oracle."""
+    n_pts = 400
+    sizes, ptrs, inds = H.ba_problem(n_pts, 60, seed=9, window=6)
+    kw = dict(computation_model=_capi.MODEL_CUDA_2080TI)
+    g = bsp.Solver.create(sizes, ptrs, inds, [0, n_pts], **kw)
+    o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, [0, n_pts], backend=_capi.BACKEND_REF, **kw)
+    for name in _capi.ARRAY_IDS:
+        np.testing.assert_array_equal(g.array(name), o.array(name), err_msg=name)
+    g.set_fused(fused)
+    ranges = list(g.array("sparseElimRanges"))
+    dense_from = int(g.lumpToSpan[ranges[-1]]) if ranges else 0
+    n_spans = g.num_spans
+    inside = int(g.lumpToSpan[(ranges[-1] + g.num_lumps) // 2])
+    cuts = sorted({int(g.lumpToSpan[r]) for r in ranges[1:]} | {dense_from, inside})
+    cuts = [c for c in cuts if 0 < c < n_spans and c <= g.can_factor_up_to_span]
+    assert len(cuts) >= 2
+    data = H.make_data(g, 11, np.float64)
+    mask = H.flat_lower_mask(g)
+    rhs = H.oapi().random_data_array(g.order * 2, -1, 1, 77).reshape(2, g.order)
+    for cut in cuts:
+        d = torch_of(data)
+        ref = data.copy()
+        g.factor(d, 0, cut)
+        o.factor(ref, 0, cut)
+        assert np.abs(d.cpu().numpy() - ref)[mask].max() <= H.TOL_FACTOR * np.abs(ref).max(), ("upTo", cut)
+        g.factor(d, cut, n_spans)
+        o.factor(ref, cut, n_spans)
+        assert np.abs(d.cpu().numpy() - ref)[mask].max() <= H.TOL_FACTOR * np.abs(ref).max(), ("from", cut)
+        for mode in (bsp.SOLVE_L, bsp.SOLVE_LT):
+            for (a, b) in ((0, cut), (cut, n_spans)):
+                x = torch_of(rhs)
+                g.solve(d, x, mode, a, b)
+                xr = rhs.copy()
+                o.solve(ref, xr, mode, a, b)
+                assert np.abs(x.cpu().numpy() - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max()), (mode, a, b)
