@@ -66,7 +66,7 @@ struct LcParams {
   unsigned* wdone;      // [nbc] inverse flags
   unsigned* ticket;
   unsigned* abortFlag;  // holds the epoch of the launch that timed out (never reset)
-  double* wbuf;         // [nbc][96 * 96] block inverses, row-major
+  double* wbuf;         // [nbc][96 * LDE] block inverses, row-major, padded rows: the epilogue's operand layout as it is
   unsigned epoch, ticketBase;
   long long* dbg;       // diagnostics (BSPB200_LUMPCHOL_DBG=1): [64][16] clock64 stamps of the diagonal jobs, then
                         // [gridDim.x][4] per-CTA cycle totals (main loop, epilogue, flag waits of the producer, jobs)
@@ -103,6 +103,11 @@ __device__ __forceinline__ void tmaLoad2D(uint32_t dst, const CUtensorMap* map, 
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void bulkLoad(uint32_t dst, const void* src, int bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ unsigned ldAcquire(const unsigned* p) {
@@ -147,6 +152,12 @@ __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, u
 // In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the nd x nd lower triangle) by the 256 consumer
 // threads: thread (warp w, lane l) owns rows l + 32 a (a < 3) x columns w + 8 u (u < 12) in registers; four columns per
 // step and two barriers (the scheme of panel2_kernel, DenseKernels.cu, without slab rows).
+// UF column slots are unrolled per loop iteration, then the finished slots are written back and the live ones shift
+// down by UF, so that register indices stay static while the code stays small: a diagonal job runs this code ONCE, on an
+// SM whose instruction cache has never seen it - fully unrolled (UF = 12, ~110 KB of straight-line code) it measured
+// 79 k cycles, instruction-fetch bound; the standalone panel kernel, where 80 CTAs fetch the same lines together, does
+// not pay that.
+template <int UF>
 __device__ __forceinline__ void potrfTile(double* S, int nd, double* colbuf, double* ybuf, int warp, int lane) {
   constexpr int NW = 8, RA = 3, CU = 12;
   double reg[RA][CU];
@@ -154,161 +165,198 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* colbuf, dou
   for (int a = 0; a < RA; a++)
 #pragma unroll
     for (int u = 0; u < CU; u++) reg[a][u] = S[(lane + 32 * a) * LDQ + warp + NW * u];
+#pragma unroll 1
+  for (int u0 = 0; u0 < CU; u0 += UF) {
+    const int rem = CU - u0;  // live slots: slot s holds column warp + 8 (u0 + s)
 #pragma unroll
-  for (int u = 0; u < CU; u++) {
+    for (int uu = 0; uu < UF; uu++) {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int j0 = NW * u + 4 * h;
-      if (j0 < nd) {
-        const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
-        if (q >= 0 && q < 4) {
+      for (int h = 0; h < 2; h++) {
+        const int j0 = NW * (u0 + uu) + 4 * h;
+        if (j0 < nd) {
+          const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (lane + 32 * a >= j0) colbuf[q * TB + lane + 32 * a] = reg[a][uu];
+          }
+          consumerBar();
+          double d[4][4], raw[RA][4];
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = c; r < 4; r++) d[r][c] = colbuf[c * TB + j0 + r];
 #pragma unroll
           for (int a = 0; a < RA; a++)
-            if (lane + 32 * a >= j0) colbuf[q * TB + lane + 32 * a] = reg[a][u];
-        }
-        consumerBar();
-        double d[4][4], raw[RA][4];
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++) raw[a][c] = (32 * a + 31 < j0) ? 0.0 : colbuf[c * TB + lane + 32 * a];
 #pragma unroll
-          for (int r = c; r < 4; r++) d[r][c] = colbuf[c * TB + j0 + r];
-#pragma unroll
-        for (int a = 0; a < RA; a++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) raw[a][c] = (32 * a + 31 < j0) ? 0.0 : colbuf[c * TB + lane + 32 * a];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          if (j0 + c >= nd) d[c][c] = 1.0;  // columns beyond the block act as identity
-        double rs[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-#pragma unroll
-          for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
-          rs[c] = rsqrtNewton(d[c][c]);
-#pragma unroll
-          for (int r = c + 1; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
-            d[r][c] *= rs[c];
-          }
-        }
-        double y[RA][4];
-#pragma unroll
-        for (int a = 0; a < RA; a++) {
-          const int t = lane + 32 * a - j0;
-          if (32 * a + 31 < j0) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) y[a][c] = 0.0;
-            continue;
-          }
+          for (int c = 0; c < 4; c++)
+            if (j0 + c >= nd) d[c][c] = 1.0;  // columns beyond the block act as identity
+          double rs[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            double v = raw[a][c];
 #pragma unroll
-            for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
-            y[a][c] = (t >= c) ? v * rs[c] : 0.0;
-          }
-        }
+            for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
+            rs[c] = rsqrtNewton(d[c][c]);
 #pragma unroll
-        for (int a = 0; a < RA; a++)
-          if (warp == a) {
+            for (int r = c + 1; r < 4; r++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
-          }
-        consumerBar();
-#pragma unroll
-        for (int sl = u; sl < CU; sl++) {
-          const int cb = NW * sl;
-          const double2 lo = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4);
-          const double2 hi = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4 + 2);
-          double yc[4] = {lo.x, lo.y, hi.x, hi.y};
-          if (sl == u && !(h == 0 && warp >= 4)) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) yc[c] = 0.0;
-          }
-#pragma unroll
-          for (int a = 0; a < RA; a++) {
-            if (j0 + 3 < 32 * a + 31 && cb <= 32 * a + 31) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) reg[a][sl] -= y[a][c] * yc[c];
+              for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
+              d[r][c] *= rs[c];
             }
           }
-        }
-        if (q >= 0 && q < 4) {
+          double y[RA][4];
+#pragma unroll
+          for (int a = 0; a < RA; a++) {
+            const int t = lane + 32 * a - j0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              double v = raw[a][c];
+#pragma unroll
+              for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
+              y[a][c] = (t >= c) ? v * rs[c] : 0.0;
+            }
+          }
 #pragma unroll
           for (int a = 0; a < RA; a++)
-            if (lane + 32 * a >= j0) reg[a][u] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+            if (warp == a) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
+            }
+          consumerBar();
+#pragma unroll
+          for (int sl = uu; sl < CU; sl++) {
+            if (UF == CU || sl < rem) {
+              const int cb = NW * (u0 + sl);
+              const double2 lo = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4);
+              const double2 hi = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4 + 2);
+              double yc[4] = {lo.x, lo.y, hi.x, hi.y};
+              if (sl == uu && !(h == 0 && warp >= 4)) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) yc[c] = 0.0;
+              }
+#pragma unroll
+              for (int a = 0; a < RA; a++) {
+                if (j0 + 3 < 32 * a + 31 && cb <= 32 * a + 31) {  // warp uniform
+#pragma unroll
+                  for (int c = 0; c < 4; c++) reg[a][sl] -= y[a][c] * yc[c];
+                }
+              }
+            }
+          }
+          if (q >= 0 && q < 4) {
+#pragma unroll
+            for (int a = 0; a < RA; a++)
+              if (lane + 32 * a >= j0) reg[a][uu] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
+          }
         }
       }
     }
+    // columns warp + 8 (u0 .. u0 + UF - 1) are final: write them back (no reader before the closing barrier), then
+    // shift the live slots down
+#pragma unroll
+    for (int uu = 0; uu < UF; uu++)
+#pragma unroll
+      for (int a = 0; a < RA; a++) S[(lane + 32 * a) * LDQ + warp + NW * (u0 + uu)] = reg[a][uu];
+    if (UF < CU) {
+#pragma unroll
+      for (int sl = 0; sl + UF < CU; sl++)
+        if (sl + UF < rem) {
+#pragma unroll
+          for (int a = 0; a < RA; a++) reg[a][sl] = reg[a][sl + UF];
+        }
+    }
   }
-  consumerBar();
-#pragma unroll
-  for (int u = 0; u < CU; u++)
-#pragma unroll
-    for (int a = 0; a < RA; a++) S[(lane + 32 * a) * LDQ + warp + NW * u] = reg[a][u];
   consumerBar();
 }
 
-// dst(32 x 32, ldd) = sign * X(32 x 32, ldx) * Y(32 x 32, ldy) (+ dst when ACC), 256 threads: thread -> row tid / 8,
-// 4 consecutive columns
-template <bool ACC>
-__device__ __forceinline__ void mm32(double* dst, int ldd, const double* X, int ldx, const double* Y, int ldy,
-                                     double sign, int tid) {
-  const int r = tid >> 3, c4 = (tid & 7) * 4;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 8
-  for (int q = 0; q < 32; q++) {
-    const double x = X[r * ldx + q];
-    const double* y = Y + q * ldy + c4;
-    a0 += x * y[0], a1 += x * y[1], a2 += x * y[2], a3 += x * y[3];
-  }
-  double* d = dst + r * ldd + c4;
-  if (ACC) {
-    d[0] += sign * a0, d[1] += sign * a1, d[2] += sign * a2, d[3] += sign * a3;
-  } else {
-    d[0] = sign * a0, d[1] = sign * a1, d[2] = sign * a2, d[3] = sign * a3;
-  }
+// One warp: dst(8 x 8, ldd) = sign * X(8 x K, ldx) * Y(K x 8, ldy), K a multiple of 4, all in shared memory (DMMA m8n8k4;
+// X row-major = the A fragment [g][t], Y row-major read as the "col" fragment: lane (g, t) takes Y[k0 + t][g]).
+__device__ __forceinline__ void tileMma(double* dst, int ldd, const double* X, int ldx, const double* Y, int ldy, int K,
+                                        double sign, int g, int t) {
+  double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+  for (int k0 = 0; k0 < K; k0 += 4) dmma(c0, c1, X[g * ldx + k0 + t], Y[(k0 + t) * ldy + g]);
+  dst[g * ldd + 2 * t] = sign * c0;
+  dst[g * ldd + 2 * t + 1] = sign * c1;
 }
 
-// W = L^-1 for the lower-triangular L in S ([96][LDQ], identity beyond nd) -> Wm ([96][LDE], zero above the diagonal),
-// blocked 3 x 3 over 32 x 32 blocks: the three diagonal inverses by forward substitution (one warp each, thread per
-// column), then W21 = -W22 (L21 W11), W32 = -W33 (L32 W22), W31 = -W33 (L31 W11 + L32 W21) with all 256 threads.
-// T ([32][LDE] x 2) is scratch.
+// W = L^-1 for the lower-triangular L in S ([96][LDQ], identity beyond nd) -> Wm ([96][LDE], zero above the diagonal).
+// Built bottom-up from block inverses, every product on the tensor pipe (this sits on the critical chain of the
+// factorization: ~5 k cycles; a thread-per-column substitution + SIMT block products measured 54 k):
+//   8 x 8 diagonal blocks by forward substitution (12 blocks x 8 columns = 96 threads, reciprocal diagonals), then for
+//   block sizes b = 8, 16, 32:  W21 = -W22 (L21 W11)  doubles the inverted diagonal blocks to 2b, and finally the 3 x 3
+//   arrangement of 32-blocks: W21, W32 as before, W31 = -W33 ([L31 L32] [W11; W21]).
+// T ([64][LDE]) is scratch for the inner products.
 __device__ __forceinline__ void invertTile(const double* S, double* Wm, double* T, int tid, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  double* dinv = T + 63 * LDE;  // last scratch row: reciprocals of the diagonal
   for (int i = tid; i < TB * LDE; i += kConsumers) Wm[i] = 0.0;
+  if (tid < TB) dinv[tid] = 1.0 / S[tid * LDQ + tid];
   consumerBar();
-  if (warp < 3) {
-    const int b0 = 32 * warp, c = lane;
-    double w[32];
+  if (tid < TB) {  // 8 x 8 diagonal blocks: thread -> (block tid / 8, column tid % 8)
+    const int b0 = (tid >> 3) * 8, c = tid & 7;
+    double w[8];
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
+    for (int i = 0; i < 8; i++) {
       double s = (i == c) ? 1.0 : 0.0;
 #pragma unroll
       for (int q = 0; q < i; q++) s -= S[(b0 + i) * LDQ + b0 + q] * w[q];
-      w[i] = (i >= c) ? s / S[(b0 + i) * LDQ + b0 + i] : 0.0;
+      w[i] = (i >= c) ? s * dinv[b0 + i] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 32; i++) Wm[(b0 + i) * LDE + b0 + c] = w[i];
+    for (int i = 0; i < 8; i++) Wm[(b0 + i) * LDE + b0 + c] = w[i];
   }
   consumerBar();
-  double* T0 = T;
-  double* T1 = T + 32 * LDE;
-  // T0 = L21 W11, T1 = L32 W22
-  mm32<false>(T0, LDE, S + 32 * LDQ, LDQ, Wm, LDE, 1.0, tid);
-  mm32<false>(T1, LDE, S + 64 * LDQ + 32, LDQ, Wm + 32 * LDE + 32, LDE, 1.0, tid);
+  // 8 -> 16: six 16-blocks, one tile each: T = L21 W11, W21 = -W22 T (the same warp does both)
+  if (warp < 6) {
+    const int o = 16 * warp;
+    double* Tb = T + warp * 8 * LDE;
+    tileMma(Tb, LDE, S + (o + 8) * LDQ + o, LDQ, Wm + o * LDE + o, LDE, 8, 1.0, g, t);
+    __syncwarp();
+    tileMma(Wm + (o + 8) * LDE + o, LDE, Wm + (o + 8) * LDE + o + 8, LDE, Tb, LDE, 8, -1.0, g, t);
+  }
+  consumerBar();
+  // 16 -> 32: three 32-blocks, 16 x 16 products (4 tiles each, 12 tiles per stage)
+  for (int tile = warp; tile < 12; tile += 8) {
+    const int o = 32 * (tile >> 2), ti = (tile >> 1) & 1, tj = tile & 1;
+    tileMma(T + (tile >> 2) * 16 * LDE + ti * 8 * LDE + tj * 8, LDE, S + (o + 16 + 8 * ti) * LDQ + o, LDQ,
+            Wm + o * LDE + o + 8 * tj, LDE, 16, 1.0, g, t);
+  }
+  consumerBar();
+  for (int tile = warp; tile < 12; tile += 8) {
+    const int o = 32 * (tile >> 2), ti = (tile >> 1) & 1, tj = tile & 1;
+    tileMma(Wm + (o + 16 + 8 * ti) * LDE + o + 8 * tj, LDE, Wm + (o + 16 + 8 * ti) * LDE + o + 16, LDE,
+            T + (tile >> 2) * 16 * LDE + tj * 8, LDE, 16, -1.0, g, t);
+  }
+  consumerBar();
+  // 32 -> 96. T0 = L21 W11 (rows 0..31 of T), T1 = L32 W22 (rows 32..63): 32 tiles
+  for (int tile = warp; tile < 32; tile += 8) {
+    const int which = tile >> 4, ti = (tile >> 2) & 3, tj = tile & 3;
+    const double* X = which ? S + (64 + 8 * ti) * LDQ + 32 : S + (32 + 8 * ti) * LDQ;
+    const double* Y = which ? Wm + 32 * LDE + 32 + 8 * tj : Wm + 8 * tj;
+    tileMma(T + (32 * which + 8 * ti) * LDE + 8 * tj, LDE, X, LDQ, Y, LDE, 32, 1.0, g, t);
+  }
   consumerBar();
   // W21 = -W22 T0, W32 = -W33 T1
-  mm32<false>(Wm + 32 * LDE, LDE, Wm + 32 * LDE + 32, LDE, T0, LDE, -1.0, tid);
-  mm32<false>(Wm + 64 * LDE + 32, LDE, Wm + 64 * LDE + 64, LDE, T1, LDE, -1.0, tid);
+  for (int tile = warp; tile < 32; tile += 8) {
+    const int which = tile >> 4, ti = (tile >> 2) & 3, tj = tile & 3;
+    const int ro = which ? 64 : 32, co = which ? 32 : 0;
+    tileMma(Wm + (ro + 8 * ti) * LDE + co + 8 * tj, LDE, Wm + (ro + 8 * ti) * LDE + ro, LDE,
+            T + 32 * which * LDE + 8 * tj, LDE, 32, -1.0, g, t);
+  }
   consumerBar();
-  // T0 = L31 W11 + L32 W21
-  mm32<false>(T0, LDE, S + 64 * LDQ, LDQ, Wm, LDE, 1.0, tid);
+  // T0 = [L31 L32] [W11; W21]  (K = 64: both operands are contiguous in k), then W31 = -W33 T0
+  for (int tile = warp; tile < 16; tile += 8) {
+    const int ti = tile >> 2, tj = tile & 3;
+    tileMma(T + 8 * ti * LDE + 8 * tj, LDE, S + (64 + 8 * ti) * LDQ, LDQ, Wm + 8 * tj, LDE, 64, 1.0, g, t);
+  }
   consumerBar();
-  mm32<true>(T0, LDE, S + 64 * LDQ + 32, LDQ, Wm + 32 * LDE, LDE, 1.0, tid);
-  consumerBar();
-  // W31 = -W33 T0
-  mm32<false>(Wm + 64 * LDE, LDE, Wm + 64 * LDE + 64, LDE, T0, LDE, -1.0, tid);
+  for (int tile = warp; tile < 16; tile += 8) {
+    const int ti = tile >> 2, tj = tile & 3;
+    tileMma(Wm + (64 + 8 * ti) * LDE + 8 * tj, LDE, Wm + (64 + 8 * ti) * LDE + 64, LDE, T + 8 * tj, LDE, 32, -1.0, g, t);
+  }
   consumerBar();
 }
 
@@ -340,6 +388,7 @@ struct LoadCtx {
   unsigned epoch;
   int rowA0, rowB0, nBTiles;
   bool ok;  // false once the launch was aborted: stop waiting for flags, keep the pipeline protocol going
+  long long waitCycles;  // diagnostics: cycles the producer lane spent waiting for source tiles
 };
 __device__ __forceinline__ void issueStage(LoadCtx& lc, int kt, unsigned q, uint32_t stagesBase, uint32_t fullBar0,
                                            uint32_t emptyBar0) {
@@ -347,7 +396,9 @@ __device__ __forceinline__ void issueStage(LoadCtx& lc, int kt, unsigned q, uint
   mbarWait(emptyBar0 + 8 * stage, parity ^ 1);  // every warp released the previous use of the slot
   if (kt % (TB / BK) == 0 && lc.ok) {           // first stage of a K block: its two source tiles must be published
     const int kb = kt / (TB / BK);
+    const long long t0 = clock64();
     lc.ok = waitFlag(lc.doneA + kb, lc.epoch, lc.abortFlag) && waitFlag(lc.doneB + kb, lc.epoch, lc.abortFlag);
+    lc.waitCycles += clock64() - t0;
     fenceProxyAsync();  // the tiles were written through the generic proxy, TMA reads through the async proxy
   }
   const uint32_t bar = fullBar0 + 8 * stage, dst = stagesBase + stage * kStageBytes;
@@ -394,15 +445,46 @@ __device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int kTiles, ui
   }
 }
 
+// x(24 x 48 per warp) = M[rbase.., :] W[cbase.., :]^T for the operands staged in E0 (M, [96][LDE]) and E1 (W): W is lower
+// triangular, so column tile j only sees k < its last column + 1
+__device__ __forceinline__ void trsmProduct(double (&x)[3][6][2], const double* E0, const double* E1, int rbase, int cbase,
+                                            int g, int t) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) x[i][j][0] = x[i][j][1] = 0.0;
+  const double* as = E0 + (rbase + g) * LDE + t;
+  const double* bs = E1 + (cbase + g) * LDE + t;
+#pragma unroll 2
+  for (int kk = 0; kk < TB; kk += 4) {
+    double af[3], bf[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
+#pragma unroll
+    for (int j = 0; j < 6; j++) bf[j] = bs[j * 8 * LDE + kk];
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      if (kk < cbase + 8 * j + 8) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) dmma(x[i][j][0], x[i][j][1], af[i], bf[j]);
+      }
+  }
+}
+
+template <int UF>
 __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_constant__ CUtensorMap tmap, LcParams p) {
   extern __shared__ __align__(1024) unsigned char smemRawLc[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smemRawLc + 1023) & ~(uintptr_t)1023);
+  // NO integer round trip on this pointer (e.g. to align it by hand): the compiler would lose the address space and
+  // turn every shared-memory access of the epilogues into a generic load / store (measured: the diagonal-block Cholesky
+  // took 80 k cycles instead of 30 k). __align__(1024) places the dynamic segment on the 1024-byte boundary the
+  // 128-byte swizzle needs; checked once below.
+  unsigned char* smem = smemRawLc;
   double* E0 = reinterpret_cast<double*>(smem + kSmemE0);
   double* E1 = reinterpret_cast<double*>(smem + kSmemE1);
   double* colbuf = reinterpret_cast<double*>(smem + kSmemCol);
   double* ybuf = reinterpret_cast<double*>(smem + kSmemY);
   const uint32_t stagesBase = smemU32(smem);
-  const uint32_t fullBar0 = smemU32(smem + kSmemBar), emptyBar0 = fullBar0 + 8 * NST;
+  const uint32_t fullBar0 = smemU32(smem + kSmemBar), emptyBar0 = fullBar0 + 8 * NST, wBar = fullBar0 + 16 * NST;
   __shared__ int jobS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = tid == 0;
@@ -413,17 +495,20 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   const int wm = warp & 3, wn = warp >> 2;
 
   if (tid == 0) {
+    if (stagesBase & 1023u) __trap();
     for (int s = 0; s < NST; s++) {
       mbarInit(fullBar0 + 8 * s, 1);
       mbarInit(emptyBar0 + 8 * s, kConsumers / 32);
     }
+    mbarInit(wBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
 #define LC_STAMP(i) \
   if (p.dbg && tid == 0 && job.diag && bi < 64) p.dbg[bi * 16 + (i)] = clock64();
-  long long cycMain = 0, cycEpi = 0, nJobs = 0;
+  long long cycMain = 0, cycEpi = 0, cycWait = 0, nJobs = 0;
+  unsigned wUses = 0;  // bulk loads of a block inverse so far (phase of wBar)
   unsigned it = 0;  // pipeline iteration counter, continues across the jobs of this CTA (producer and consumers agree)
   double* __restrict__ A = p.A;
   const int64_t ld = p.ld;
@@ -449,16 +534,28 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     lc.tmap = &tmap, lc.doneA = p.done + (int64_t)bi * p.nbc, lc.doneB = p.done + (int64_t)(c < 0 ? 0 : c) * p.nbc;
     lc.abortFlag = p.abortFlag, lc.epoch = p.epoch, lc.rowA0 = rowA0, lc.rowB0 = rowB0, lc.nBTiles = job.diag ? 2 : 1;
     lc.ok = *(volatile unsigned*)p.abortFlag != p.epoch;
+    lc.waitCycles = 0;
     if (job.diag)
       mainLoop<12>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 96 * wn, g, t, lane, producer, lc);
     else
       mainLoop<6>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane, producer, lc);
     __syncthreads();  // (A) every stage has been consumed: the stage memory becomes the epilogue workspace
     const long long tMain = clock64();
+    cycWait += lc.waitCycles;
     LC_STAMP(1)
 
     const int nc = c >= 0 ? min(TB, p.n - c * TB) : 0;  // valid columns of block column c
-    const bool aborted = *(volatile unsigned*)p.abortFlag == p.epoch;
+    if (tid == 0 && c >= 0) {
+      // W_c -> E1 by one bulk copy (the buffer holds the padded operand layout), in flight while M is staged
+      if (*(volatile unsigned*)p.abortFlag != p.epoch) {
+        const long long t0 = clock64();
+        waitFlag(p.wdone + c, p.epoch, p.abortFlag);
+        cycWait += clock64() - t0;
+      }
+      fenceProxyAsync();
+      mbarArriveExpectTx(wBar, TB * LDE * 8);
+      bulkLoad(smemU32(E1), p.wbuf + (int64_t)c * TB * LDE, TB * LDE * 8, wBar);
+    }
 
     if (!job.diag) {
       // ---- regular tile: M = A(i,c) - acc -> E0 ; W_c -> E1 ; X = M W^T -> global
@@ -473,37 +570,11 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
           if (gr < p.rows && cc < nc) a = *reinterpret_cast<const double2*>(A + gr * ld + c * TB + cc);
           *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
         }
-      if (tid == 0 && !aborted) waitFlag(p.wdone + c, p.epoch, p.abortFlag);
       consumerBar();
-      {
-        const double* __restrict__ W = p.wbuf + (int64_t)c * TB * TB;
-        for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
-          const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
-          *reinterpret_cast<double2*>(E1 + r * LDE + c2) = __ldcg(reinterpret_cast<const double2*>(W + r * TB + c2));
-        }
-      }
-      consumerBar();
+      mbarWait(wBar, wUses & 1);  // W_c has landed in E1 (requested by thread 0 right after the main loop)
+      wUses++;
       double x[3][6][2];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 6; j++) x[i][j][0] = x[i][j][1] = 0.0;
-      const double* as = E0 + (rbase + g) * LDE + t;
-      const double* bs = E1 + (cbase + g) * LDE + t;
-#pragma unroll 2
-      for (int kk = 0; kk < TB; kk += 4) {
-        double af[3], bf[6];
-#pragma unroll
-        for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
-#pragma unroll
-        for (int j = 0; j < 6; j++) bf[j] = bs[j * 8 * LDE + kk];
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (kk < cbase + 8 * j + 8) {  // W is lower triangular: column tile j only sees k < its last column + 1
-#pragma unroll
-            for (int i = 0; i < 3; i++) dmma(x[i][j][0], x[i][j][1], af[i], bf[j]);
-          }
-      }
+      trsmProduct(x, E0, E1, rbase, cbase, g, t);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -522,12 +593,16 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       continue;
     }
 
-    // ---- diagonal job of block d = bi: tiles T1 = (d, d-1) (warps wn = 0) and T2 = (d, d) (warps wn = 1)
+    // ---- diagonal job of block d = bi: tiles T1 = (d, d-1) (accumulated by the warps wn = 0) and T2 = (d, d) (wn = 1)
     const int d = bi;
     const int nd = min(TB, p.n - d * TB);  // valid rows / columns of the diagonal block
     const int rbase = 24 * wm;
-    if (c >= 0) {
-      if (wn == 0) {
+    double* S = E1;                                               // [96][LDQ] diagonal block, once W is dead
+    double* Pk = reinterpret_cast<double*>(smem + kSmemT);        // packed lower 8 x 8 tiles of A(d,d) - acc2 (40 KB)
+    // 1. everything that does not need W_{d-1}: M1 = A(d,d-1) - acc1 -> E0 (operand of the triangular product) and
+    //    P = A(d,d) - acc2 -> packed tiles (the original entries are fetched here, off the critical chain)
+    if (wn == 0) {
+      if (c >= 0) {
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -538,100 +613,87 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
             *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
           }
       }
-      if (tid == 0 && !aborted) waitFlag(p.wdone + c, p.epoch, p.abortFlag);
-      consumerBar();
-      LC_STAMP(2)
-      {
-        const double* __restrict__ W = p.wbuf + (int64_t)c * TB * TB;
-        for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
-          const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
-          *reinterpret_cast<double2*>(E1 + r * LDE + c2) = __ldcg(reinterpret_cast<const double2*>(W + r * TB + c2));
-        }
-      }
-      consumerBar();
-      LC_STAMP(3)
-      if (wn == 0) {  // X = M W^T, 24 x 96 per warp, into the registers that held acc1
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 12; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-        const double* as = E0 + (rbase + g) * LDE + t;
-        const double* bs = E1 + g * LDE + t;
-#pragma unroll 1
-        for (int kk = 0; kk < TB; kk += 4) {
-          double af[3], bf[12];
-#pragma unroll
-          for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
-#pragma unroll
-          for (int j = 0; j < 12; j++) bf[j] = bs[j * 8 * LDE + kk];
-#pragma unroll
-          for (int j = 0; j < 12; j++)
-            if (kk < 8 * j + 8) {
-#pragma unroll
-              for (int i = 0; i < 3; i++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
-        }
-      }
-      consumerBar();  // every read of M is done: E0 becomes L1 = L(d, d-1)
-      LC_STAMP(4)
-      if (wn == 0) {
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 12; j++) {
-            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
-            const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-            *reinterpret_cast<double2*>(E0 + r * LDE + cc) = v;
-            if (rowA0 + r < p.rows) *reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc) = v;
-          }
-        __threadfence();
-        fenceProxyAsync();
-      }
-      consumerBar();
-      if (tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
-      LC_STAMP(5)
-      if (wn == 1) {  // acc2 += L1 L1^T on the lower triangle of the tile
-        const double* as = E0 + (rbase + g) * LDE + t;
-        const double* bs = E0 + g * LDE + t;
-#pragma unroll 1
-        for (int kk = 0; kk < TB; kk += 4) {
-          double af[3], bf[12];
-#pragma unroll
-          for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
-#pragma unroll
-          for (int j = 0; j < 12; j++) bf[j] = bs[j * 8 * LDE + kk];
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 12; j++)
-              if (8 * j <= rbase + 8 * i + 7) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-      }
-    }
-    // D = A(d,d) - acc2 -> S (= E1 region as [96][LDQ]); the W^T operand in E1 is dead (all warps passed the barrier
-    // after the X product); zero outside the valid lower triangle
-    double* S = E1;
-    consumerBar();
-    LC_STAMP(6)
-    for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
-    consumerBar();
-    if (wn == 1) {
-      // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along the
-      // factorization as the extra rows of a trapezoid: they come out as M L^-T
+    } else {
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 12; j++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t + e;
-            if (cc <= r && cc < nd && rowA0 + r < p.rows)
-              S[r * LDQ + cc] = A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] - acc[i][j][e];
+        for (int j = 0; j < 12; j++) {
+          const int ti = 3 * wm + i;
+          if (j <= ti) {  // lower tiles only (warp uniform)
+            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
+            double2 a = make_double2(0.0, 0.0);
+            if (cc < nd && rowA0 + r < p.rows)
+              a = *reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc);
+            *reinterpret_cast<double2*>(Pk + (ti * (ti + 1) / 2 + j) * 64 + g * 8 + 2 * t) =
+                make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
           }
+        }
+    }
+    LC_STAMP(2)
+    consumerBar();
+    if (c >= 0) {
+      // 2. L1 = L(d,d-1) = M1 W^T by all eight warps (24 x 48 each)
+      mbarWait(wBar, wUses & 1);
+      wUses++;
+      LC_STAMP(3)
+      double x[3][6][2];
+      const int cbase = 48 * wn;
+      trsmProduct(x, E0, E1, rbase, cbase, g, t);
+      consumerBar();  // every read of M1 and W is done: E0 becomes L1, E1 becomes the diagonal block
+      LC_STAMP(4)
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const double2 v = make_double2(x[i][j][0], x[i][j][1]);
+          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = v;
+          if (rowA0 + r < p.rows) *reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc) = v;
+        }
+      __threadfence();
+    }
+    for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
+    consumerBar();
+    if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+    LC_STAMP(5)
+    // 3. D = P - L1 L1^T on the 78 lower tiles, spread over the eight warps (tile tt -> warp tt mod 8), straight into S
+    {
+      double y[10][2];
+      int rowI[10], rowJ[10];  // tile tt = ti (ti + 1) / 2 + tj  ->  first rows of its two operands
+#pragma unroll
+      for (int q = 0; q < 10; q++) {
+        y[q][0] = y[q][1] = 0.0;
+        const int tt = min(warp + 8 * q, 77);
+        int ti = (int)((sqrtf(8.0f * tt + 1.0f) - 1.0f) * 0.5f);
+        ti += ((ti + 1) * (ti + 2) / 2 <= tt) ? 1 : 0;
+        ti -= (ti * (ti + 1) / 2 > tt) ? 1 : 0;
+        rowI[q] = 8 * ti, rowJ[q] = 8 * (tt - ti * (ti + 1) / 2);
+      }
+      if (c >= 0) {
+#pragma unroll 1
+        for (int kk = 0; kk < TB; kk += 4) {
+#pragma unroll
+          for (int q = 0; q < 10; q++)
+            if (warp + 8 * q < 78)
+              dmma(y[q][0], y[q][1], E0[(rowI[q] + g) * LDE + kk + t], E0[(rowJ[q] + g) * LDE + kk + t]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 10; q++) {
+        const int tt = warp + 8 * q;
+        if (tt < 78) {
+          const double2 pv = *reinterpret_cast<const double2*>(Pk + tt * 64 + g * 8 + 2 * t);
+          const int r = rowI[q] + g, cc = rowJ[q] + 2 * t;
+          // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along
+          // the factorization as the extra rows of a trapezoid: they come out as M L^-T
+          if (cc <= r && cc < nd && rowA0 + r < p.rows) S[r * LDQ + cc] = pv.x - y[q][0];
+          if (cc + 1 <= r && cc + 1 < nd && rowA0 + r < p.rows) S[r * LDQ + cc + 1] = pv.y - y[q][1];
+        }
+      }
     }
     consumerBar();
     LC_STAMP(7)
-    potrfTile(S, nd, colbuf, ybuf, warp, lane);
+    potrfTile<UF>(S, nd, colbuf, ybuf, warp, lane);
     LC_STAMP(8)
     if (nd < TB) {
       // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion
@@ -654,11 +716,9 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     if (d + 1 < p.nbr) {  // somebody below needs W_d = L(d,d)^-1: first, it is on the critical path
       invertTile(S, E0, reinterpret_cast<double*>(smem + kSmemT), tid, warp, lane);
       LC_STAMP(9)
-      double* __restrict__ W = p.wbuf + (int64_t)d * TB * TB;
-      for (int idx = tid; idx < TB * TB / 2; idx += kConsumers) {
-        const int r = idx / (TB / 2), c2 = (idx % (TB / 2)) * 2;
-        *reinterpret_cast<double2*>(W + r * TB + c2) = *reinterpret_cast<const double2*>(E0 + r * LDE + c2);
-      }
+      double* __restrict__ W = p.wbuf + (int64_t)d * TB * LDE;
+      for (int idx = tid; idx < TB * LDE / 2; idx += kConsumers)
+        *reinterpret_cast<double2*>(W + 2 * idx) = *reinterpret_cast<const double2*>(E0 + 2 * idx);
       __threadfence();
       consumerBar();
       if (tid == 0) stRelease(p.wdone + d, p.epoch);
@@ -679,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
 #undef LC_STAMP
   if (p.dbg && tid == 0) {
     long long* q = p.dbg + 64 * 16 + (int64_t)blockIdx.x * 4;
-    q[0] = cycMain, q[1] = cycEpi, q[2] = 0, q[3] = nJobs;
+    q[0] = cycMain, q[1] = cycEpi, q[2] = cycWait, q[3] = nJobs;
   }
   if (tid == 0 && *(volatile unsigned*)p.abortFlag == p.epoch) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -767,7 +827,7 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
     s.nbcCap = std::max(p.nbc, s.nbcCap * 2);
     s.tileCap = std::max(tiles, s.tileCap * 2);
     s.words.resize((size_t)(2 + s.nbcCap + s.tileCap));
-    s.wbuf.resize((size_t)s.nbcCap * TB * TB);
+    s.wbuf.resize((size_t)s.nbcCap * TB * LDE);
     B200_CUDA(cudaMemsetAsync(s.words.ptr(), 0, s.words.size() * sizeof(unsigned), st));
     s.epoch = 0, s.ticketBase = 0;
   }
@@ -797,10 +857,29 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   int dev = 0, sms = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = (int)std::min<int64_t>(sms, jobs);
-  ensureDynSmem((const void*)lump_chol_kernel, kSmemBytes);
-  ProfScope prof(st, KC_LUMP_CHOL, (double)n * n * n / 3 + (double)rowsBelow * n * n, 0);
-  lump_chol_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
+  // CTAs: the chain of diagonal blocks bounds the run time from below (~40 us per block column); more CTAs than it
+  // takes to finish the flops in that time only spin on flags - and occupy SMs that lumps factored concurrently on
+  // other streams (independent lumps of a tree level) could use. 1.5 x the break-even count, at ~200 GF/s per SM.
+  const double flops = (double)n * n * n / 3 + (double)rowsBelow * n * n;
+  int64_t want = (int64_t)(1.5 * flops / (p.nbc * 40e-6 * 200e9)) + 1;
+  if (const char* e = getenv("BSPB200_LUMPCHOL_GRID")) want = atoi(e);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)sms, jobs, std::max<int64_t>(want, 16)}));
+  ProfScope prof(st, KC_LUMP_CHOL, flops, 0);
+  // column slots of the diagonal-block Cholesky unrolled per loop iteration (BSPB200_LUMPCHOL_UF: 1, 2, 3, 4, 6, 12)
+  const char* ufe = getenv("BSPB200_LUMPCHOL_UF");
+  const int uf = ufe ? atoi(ufe) : 2;
+  auto launch = [&](auto kern) {
+    ensureDynSmem((const void*)kern, kSmemBytes);
+    kern<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
+  };
+  switch (uf) {
+    case 1: launch(lump_chol_kernel<1>); break;
+    case 3: launch(lump_chol_kernel<3>); break;
+    case 4: launch(lump_chol_kernel<4>); break;
+    case 6: launch(lump_chol_kernel<6>); break;
+    case 12: launch(lump_chol_kernel<12>); break;
+    default: launch(lump_chol_kernel<2>); break;
+  }
   B200_LAUNCH_CHECK();
   s.ticketBase += (unsigned)(jobs + grid);
   return true;

@@ -18,51 +18,55 @@ M = torch.randn(n, n, dtype=torch.float64, device="cuda")
 A11 = M @ M.T + n * torch.eye(n, dtype=torch.float64, device="cuda")
 A = torch.cat([A11, torch.randn(rb, n, dtype=torch.float64, device="cuda")]).contiguous()
 st = torch.cuda.current_stream().cuda_stream
-os.environ["BSPB200_LUMPCHOL"] = "1"
-W = A.clone()
-for rep in range(3):
-    W.copy_(A)
-    api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
-torch.cuda.synchronize()
-ts = []
-for rep in range(5):
-    W.copy_(A)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
-    e1.record()
+ufs = os.environ.get("PROBE_UFS", "2").split(",")
+for uf in ufs:
+    os.environ["BSPB200_LUMPCHOL_UF"] = uf
+    print("==== UF", uf)
+    os.environ["BSPB200_LUMPCHOL"] = "1"
+    W = A.clone()
+    for rep in range(3):
+        W.copy_(A)
+        api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
     torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-print("ms (min, median):", min(ts), sorted(ts)[2])
-os.environ["BSPB200_LUMPCHOL_DBG"] = "1"
-W.copy_(A)
-api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
-torch.cuda.synchronize()
-buf = np.zeros(64 * 16 + 1024 * 4, dtype=np.int64)
-got = api.debug_read(1, buf.ctypes.data_as(C.c_void_p), buf.nbytes)
-os.environ["BSPB200_LUMPCHOL_DBG"] = "0"
-st_ = buf[:64 * 16].reshape(64, 16)
-names = ["mainloop", "wait_W", "load_W", "trsm", "store_L1", "syrk", "zero_S", "D_to_S", "potrf", "invert", "W_store", "L_store"]
-nb = (n + 95) // 96
-rows = []
-for d in range(1, min(nb, 64)):
-    s = st_[d]
-    if s[0] == 0:
-        continue
-    dif = [int(s[i + 1] - s[i]) if s[i + 1] and s[i] else 0 for i in range(11)]
-    rows.append(dif)
-rows = np.array(rows)
-print("diag jobs:", len(rows))
-print("phase (mean cycles over diag jobs):")
-for i, nm in enumerate(names[:11]):
-    print(f"  {nm:10s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
-chain = rows[:, 1:10].sum(axis=1)
-print("chain after the main loop (wait_W .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
-# W_d flag time differences between consecutive diag jobs = the realized chain step
-w10 = st_[1:nb, 10]
-w10 = w10[w10 > 0]
-print("W flag to W flag (cycles): mean", np.diff(w10).mean(), "=", np.diff(w10).mean() / 1.965e3, "us per block column")
-cta = buf[64 * 16:].reshape(1024, 4)
-cta = cta[cta[:, 3] > 0]
-print("CTAs:", len(cta), "jobs/CTA mean", cta[:, 3].mean(), "main loop cycles mean", cta[:, 0].mean(), "epilogue cycles mean", cta[:, 1].mean(),
-      "total", (cta[:, 0] + cta[:, 1]).mean(), "=", (cta[:, 0] + cta[:, 1]).mean() / 1.965e6, "ms busy per CTA")
+    ts = []
+    for rep in range(5):
+        W.copy_(A)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("ms (min, median):", min(ts), sorted(ts)[2])
+    os.environ["BSPB200_LUMPCHOL_DBG"] = "1"
+    W.copy_(A)
+    api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
+    torch.cuda.synchronize()
+    buf = np.zeros(64 * 16 + 1024 * 4, dtype=np.int64)
+    got = api.debug_read(1, buf.ctypes.data_as(C.c_void_p), buf.nbytes)
+    os.environ["BSPB200_LUMPCHOL_DBG"] = "0"
+    st_ = buf[:64 * 16].reshape(64, 16)
+    names = ["mainloop", "wait_W", "load_W", "trsm", "store_L1", "syrk", "zero_S", "D_to_S", "potrf", "invert", "W_store", "L_store"]
+    nb = (n + 95) // 96
+    rows = []
+    for d in range(1, min(nb, 64)):
+        s = st_[d]
+        if s[0] == 0:
+            continue
+        dif = [int(s[i + 1] - s[i]) if s[i + 1] and s[i] else 0 for i in range(11)]
+        rows.append(dif)
+    rows = np.array(rows)
+    print("diag jobs:", len(rows))
+    print("phase (mean cycles over diag jobs):")
+    for i, nm in enumerate(names[:11]):
+        print(f"  {nm:10s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
+    chain = rows[:, 1:10].sum(axis=1)
+    print("chain after the main loop (wait_W .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
+    # W_d flag time differences between consecutive diag jobs = the realized chain step
+    w10 = st_[1:nb, 10]
+    w10 = w10[w10 > 0]
+    print("W flag to W flag (cycles): mean", np.diff(w10).mean(), "=", np.diff(w10).mean() / 1.965e3, "us per block column")
+    cta = buf[64 * 16:].reshape(1024, 4)
+    cta = cta[cta[:, 3] > 0]
+    print("CTAs:", len(cta), "jobs/CTA mean", cta[:, 3].mean(), "main loop cycles mean", cta[:, 0].mean(), "epilogue cycles mean", cta[:, 1].mean(), "flag-wait cycles mean", cta[:, 2].mean(),
+          "total", (cta[:, 0] + cta[:, 1]).mean(), "=", (cta[:, 0] + cta[:, 1]).mean() / 1.965e6, "ms busy per CTA")
