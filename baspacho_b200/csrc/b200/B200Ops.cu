@@ -8,6 +8,7 @@
 //   * no host<->device traffic inside factor()/solve() except the batch pointer array when it changes
 //     (reference: numSpans*8 bytes H2D per lump in prepareAssemble :471-481, pointer arrays before every op);
 //   * errors are std::runtime_error, never abort() (reference: CudaDefs.h:27-65).
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -279,6 +280,68 @@ struct B200SymbolicCtx : SymbolicCtx {
     }
     return *belowRowsPtr;
   }
+  // ---- fragmented skeletons (every lump a single span of at most 32 scalars): row lists for the gathers and the levels
+  // of the block dependency graph for the two substitution directions (built once)
+  struct FragPlan {
+    bool eligible = false;
+    DevBuf<int32_t> rowPtr, rowCol, lvlL, lvlT, tailList;
+    DevBuf<int64_t> rowOff;
+    vector<int32_t> lvlPtrL, lvlPtrT;    // per level (+1) into lvlL / lvlT
+    vector<int32_t> hostLvlL, hostLvlT;  // span lists, ascending inside a level
+    FragDev dev;
+    double nnz = 0;
+  };
+  std::unique_ptr<FragPlan> fragPlanPtr;
+  const FragPlan& fragPlan() {
+    if (!fragPlanPtr) {
+      auto p = std::make_unique<FragPlan>();
+      const int64_t ns = skel.numSpans();
+      bool ok = ns == skel.numLumps() && ns > 0 && ns < (int64_t(1) << 31) && skel.dataSize() < (int64_t(1) << 62);
+      for (int64_t s = 0; ok && s < ns; s++) ok = skel.spanStart[s + 1] - skel.spanStart[s] <= 32;
+      if (ok) {
+        vector<int32_t> cnt(ns + 1, 0), lvF(ns, 0), lvB(ns, 0);
+        for (int64_t c = 0; c < ns; c++)
+          for (int64_t q = skel.chainColPtr[c] + 1; q < skel.chainColPtr[c + 1]; q++) cnt[skel.chainRowSpan[q] + 1]++;
+        for (int64_t s = 0; s < ns; s++) cnt[s + 1] += cnt[s];
+        vector<int32_t> rowCol(cnt[ns]), cur(cnt.begin(), cnt.end() - 1);
+        vector<int64_t> rowOff(cnt[ns]);
+        for (int64_t c = 0; c < ns; c++) {
+          const double w = (double)(skel.spanStart[c + 1] - skel.spanStart[c]);
+          p->nnz += w * (w + 1) / 2;
+          for (int64_t q = skel.chainColPtr[c] + 1; q < skel.chainColPtr[c + 1]; q++) {
+            const int64_t r = skel.chainRowSpan[q];
+            rowCol[cur[r]] = (int32_t)c, rowOff[cur[r]++] = skel.chainData[q];
+            lvF[r] = std::max(lvF[r], lvF[c] + 1);  // columns ascending: lvF[c] is final
+            p->nnz += w * (double)(skel.spanStart[r + 1] - skel.spanStart[r]);
+          }
+        }
+        for (int64_t c = ns - 1; c >= 0; c--)
+          for (int64_t q = skel.chainColPtr[c] + 1; q < skel.chainColPtr[c + 1]; q++)
+            lvB[c] = std::max(lvB[c], lvB[skel.chainRowSpan[q]] + 1);
+        auto group = [&](const vector<int32_t>& lv, vector<int32_t>& ptr, vector<int32_t>& list) {
+          const int32_t nl = ns ? *std::max_element(lv.begin(), lv.end()) + 1 : 0;
+          ptr.assign(nl + 1, 0);
+          for (int64_t s = 0; s < ns; s++) ptr[lv[s] + 1]++;
+          for (int32_t l = 0; l < nl; l++) ptr[l + 1] += ptr[l];
+          list.resize(ns);
+          vector<int32_t> at(ptr.begin(), ptr.end() - 1);
+          for (int64_t s = 0; s < ns; s++) list[at[lv[s]]++] = (int32_t)s;
+        };
+        group(lvF, p->lvlPtrL, p->hostLvlL);
+        group(lvB, p->lvlPtrT, p->hostLvlT);
+        vector<int32_t> all(ns);
+        for (int64_t s = 0; s < ns; s++) all[s] = (int32_t)s;
+        p->rowPtr.upload(cnt), p->rowCol.upload(rowCol.empty() ? vector<int32_t>(1, 0) : rowCol);
+        p->rowOff.upload(rowOff.empty() ? vector<int64_t>(1, 0) : rowOff);
+        p->lvlL.upload(p->hostLvlL), p->lvlT.upload(p->hostLvlT), p->tailList.upload(all);
+        p->dev.rowPtr = p->rowPtr.ptr(), p->dev.rowCol = p->rowCol.ptr(), p->dev.rowOff = p->rowOff.ptr();
+        p->eligible = true;
+      }
+      fragPlanPtr = std::move(p);
+    }
+    return *fragPlanPtr;
+  }
+
   ChainSync chain;
   DevBuf<unsigned> chainBuf;
   int chainBatch = 0;
@@ -663,6 +726,47 @@ struct B200SolveCtx : SolveCtx<TT> {
     }
   }
   Work<T> temp2() { return temp(1); }
+
+  // ---- fragmented whole-range ops (reference MatOps.h:168-183, MatOpsFast.cpp:613-1018): level-scheduled block
+  // kernels when every lump is a single small span and nRHS == 1 (SparseKernels.cu)
+  bool hasFragmentedOps() override { return nRHS == 1 && sym.fragPlan().eligible; }
+
+  void fragmentedMV(const TT* data, const TT* x, int64_t spanBegin, int64_t spanEnd, TT* y, T alpha) override {
+    const auto& fp = sym.fragPlan();
+    Mats<T> m = mats.get(data, sym.stream), vx = vecs.get(x, sym.stream), vy = vecs2.get(y, sym.stream);
+    fragMV<T>(sym.stream, m.batch, fp.dev, sym.dsk, m, vx, vy, spanBegin, spanEnd, alpha, fp.nnz * sizeof(T));
+  }
+
+  void fragmentedSolveL(const TT* data, int64_t spanBegin, int64_t spanEnd, TT* y) override {
+    const auto& fp = sym.fragPlan();
+    Mats<T> m = mats.get(data, sym.stream), vy = vecs.get(y, sym.stream);
+    ProfScope prof(sym.stream, KC_SOLVE_DENSE, 0, fp.nnz * sizeof(T) * m.batch);
+    for (size_t l = 0; l + 1 < fp.lvlPtrL.size(); l++) {
+      // the spans of a level are stored ascending: those inside [spanBegin, spanEnd) are one contiguous piece
+      const int32_t* b = fp.hostLvlL.data() + fp.lvlPtrL[l];
+      const int32_t* e = fp.hostLvlL.data() + fp.lvlPtrL[l + 1];
+      const int32_t* lo = std::lower_bound(b, e, (int32_t)spanBegin);
+      const int32_t* hi = std::lower_bound(lo, e, (int32_t)spanEnd);
+      fragSolveLLevel<T>(sym.stream, m.batch, fp.dev, sym.dsk, m, vy, fp.lvlL.ptr() + (lo - fp.hostLvlL.data()),
+                         (int)(hi - lo), spanBegin, spanEnd, true);
+    }
+    // rows behind the range receive the updates of its columns (no diagonal solve)
+    fragSolveLLevel<T>(sym.stream, m.batch, fp.dev, sym.dsk, m, vy, fp.tailList.ptr() + spanEnd,
+                       (int)(skel.numSpans() - spanEnd), spanBegin, spanEnd, false);
+  }
+
+  void fragmentedSolveLt(const TT* data, int64_t spanBegin, int64_t spanEnd, TT* y) override {
+    const auto& fp = sym.fragPlan();
+    Mats<T> m = mats.get(data, sym.stream), vy = vecs.get(y, sym.stream);
+    ProfScope prof(sym.stream, KC_SOLVE_DENSE, 0, fp.nnz * sizeof(T) * m.batch);
+    for (size_t l = 0; l + 1 < fp.lvlPtrT.size(); l++) {
+      const int32_t* b = fp.hostLvlT.data() + fp.lvlPtrT[l];
+      const int32_t* e = fp.hostLvlT.data() + fp.lvlPtrT[l + 1];
+      const int32_t* lo = std::lower_bound(b, e, (int32_t)spanBegin);
+      const int32_t* hi = std::lower_bound(lo, e, (int32_t)spanEnd);
+      fragSolveLtLevel<T>(sym.stream, m.batch, sym.dsk, m, vy, fp.lvlT.ptr() + (lo - fp.hostLvlT.data()), (int)(hi - lo));
+    }
+  }
 
   void sparseElimSolveL(const SymElimCtx& elimData, const TT* data, int64_t lumpsBegin, int64_t lumpsEnd, TT* C,
                         int64_t ldc) override {

@@ -53,6 +53,22 @@ struct DevElimPlan {
   const int16_t* rowChainK;
 };
 
+// row view of a fragmented skeleton (every lump one span): per span the blocks found in its row, column ascending
+struct FragDev {
+  const int32_t* rowPtr;  // per span (+1)
+  const int32_t* rowCol;  // column span of the block
+  const int64_t* rowOff;  // data offset of the block (rows(span) x cols(column span), row-major)
+};
+template <typename T>
+void fragMV(cudaStream_t st, int batch, const FragDev& f, const DevSkel& sk, Mats<T> data, Mats<T> x, Mats<T> y,
+            int64_t spanBegin, int64_t spanEnd, T alpha, double bytes);
+template <typename T>
+void fragSolveLLevel(cudaStream_t st, int batch, const FragDev& f, const DevSkel& sk, Mats<T> data, Mats<T> y,
+                     const int32_t* list, int count, int64_t spanBegin, int64_t spanEnd, bool diag);
+template <typename T>
+void fragSolveLtLevel(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, Mats<T> y, const int32_t* list,
+                      int count);
+
 // step 1 of the sparse elimination: per lump, Cholesky of the diagonal block + X L^T = B on the rows below
 template <typename T>
 void elimFactorLumps(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, int64_t lumpsBegin, int64_t lumpsEnd,

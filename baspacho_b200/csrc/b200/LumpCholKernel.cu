@@ -46,7 +46,7 @@ constexpr int kThreads = kConsumers;   // round the CTA up to 12 warps of regist
 constexpr int kTileBytes = TB * BK * 8;    // 12288: one 96-row operand tile of a stage
 constexpr int kStageBytes = 3 * kTileBytes;  // A (96 rows) + B (up to 192 rows)
 constexpr int LDE = 100;               // row stride (doubles) of the epilogue operands: [row][k], conflict-free fragments
-constexpr int LDQ = 97;                // row stride of the diagonal block staging (odd: lanes walking down rows)
+constexpr int LDQ = LDE;               // row stride of the diagonal block staging (DMMA fragments read it too)
 constexpr int kSmemE0 = 0;                            // [96][LDE]  M / L(d,d-1)            76800 B
 constexpr int kSmemE1 = TB * LDE * 8;                 // [96][LDE]  W^T operand / [96][LDQ] diagonal block
 constexpr int kSmemCol = 2 * TB * LDE * 8;            // [4][96] raw columns of the potrf step
@@ -61,13 +61,15 @@ struct LcParams {
   int64_t ld;
   int n, rows;          // lump width, total rows (n + rowsBelow)
   int nbc, nbr;         // block columns / block rows
-  int numJobs;
+  int numRegular;       // off-diagonal tiles that are not the sub-diagonal partner of a diagonal block
+  int chainCtas;        // the first chainCtas CTAs to arrive work through the diagonal jobs, in order
   unsigned* done;       // [nbr * nbc] tile flags (epoch valued)
   unsigned* wdone;      // [nbc] inverse flags
-  unsigned* ticket;
+  unsigned* ctr;        // [0] ticket of the regular jobs, [2] arrival counter, [3] ticket of the diagonal jobs (never reset)
+  unsigned ticketBase, arriveBase, diagBase;
   unsigned* abortFlag;  // holds the epoch of the launch that timed out (never reset)
   double* wbuf;         // [nbc][96 * LDE] block inverses, row-major, padded rows: the epilogue's operand layout as it is
-  unsigned epoch, ticketBase;
+  unsigned epoch;
   long long* dbg;       // diagnostics (BSPB200_LUMPCHOL_DBG=1): [64][16] clock64 stamps of the diagonal jobs, then
                         // [gridDim.x][4] per-CTA cycle totals (main loop, epilogue, flag waits of the producer, jobs)
 };
@@ -149,126 +151,151 @@ __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, u
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal block
-// In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the nd x nd lower triangle) by the 256 consumer
-// threads: thread (warp w, lane l) owns rows l + 32 a (a < 3) x columns w + 8 u (u < 12) in registers; four columns per
-// step and two barriers (the scheme of panel2_kernel, DenseKernels.cu, without slab rows).
-// UF column slots are unrolled per loop iteration, then the finished slots are written back and the live ones shift
-// down by UF, so that register indices stay static while the code stays small: a diagonal job runs this code ONCE, on an
-// SM whose instruction cache has never seen it - fully unrolled (UF = 12, ~110 KB of straight-line code) it measured
-// 79 k cycles, instruction-fetch bound; the standalone panel kernel, where 80 CTAs fetch the same lines together, does
-// not pay that.
-template <int UF>
-__device__ __forceinline__ void potrfTile(double* S, int nd, double* colbuf, double* ybuf, int warp, int lane) {
-  constexpr int NW = 8, RA = 3, CU = 12;
-  double reg[RA][CU];
+// 8 x 8 diagonal tile at D (row stride LDQ): every lane of the calling warp factors it redundantly in registers (36
+// broadcast loads; the eight dependent rsqrt of the pivots are the serial part of the whole factorization), the tile goes
+// back in place and the factor (row-major, 8 x 8) + the reciprocal pivots go to `fac` ([64 + 8]) for the panel solves.
+// e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
+__device__ __forceinline__ void factorTile8(double* D, int e, double* fac, int lane) {
+  double L8[8][8], rs[8];
 #pragma unroll
-  for (int a = 0; a < RA; a++)
+  for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int u = 0; u < CU; u++) reg[a][u] = S[(lane + 32 * a) * LDQ + warp + NW * u];
-#pragma unroll 1
-  for (int u0 = 0; u0 < CU; u0 += UF) {
-    const int rem = CU - u0;  // live slots: slot s holds column warp + 8 (u0 + s)
+    for (int c = 0; c <= i; c++) L8[i][c] = D[i * LDQ + c];
 #pragma unroll
-    for (int uu = 0; uu < UF; uu++) {
+  for (int c = 0; c < 8; c++) {
+    if (c < e) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int j0 = NW * (u0 + uu) + 4 * h;
-        if (j0 < nd) {
-          const int q = warp - 4 * h;  // owner warps of the group: q in [0, 4)
-          if (q >= 0 && q < 4) {
+      for (int k = 0; k < c; k++) L8[c][c] -= L8[c][k] * L8[c][k];
+      rs[c] = rsqrtNewton(L8[c][c]);
+      L8[c][c] *= rs[c];
 #pragma unroll
-            for (int a = 0; a < RA; a++)
-              if (lane + 32 * a >= j0) colbuf[q * TB + lane + 32 * a] = reg[a][uu];
-          }
-          consumerBar();
-          double d[4][4], raw[RA][4];
+      for (int r = c + 1; r < 8; r++) {
 #pragma unroll
-          for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int r = c; r < 4; r++) d[r][c] = colbuf[c * TB + j0 + r];
-#pragma unroll
-          for (int a = 0; a < RA; a++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) raw[a][c] = (32 * a + 31 < j0) ? 0.0 : colbuf[c * TB + lane + 32 * a];
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            if (j0 + c >= nd) d[c][c] = 1.0;  // columns beyond the block act as identity
-          double rs[4];
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-#pragma unroll
-            for (int k = 0; k < c; k++) d[c][c] -= d[c][k] * d[c][k];
-            rs[c] = rsqrtNewton(d[c][c]);
-#pragma unroll
-            for (int r = c + 1; r < 4; r++) {
-#pragma unroll
-              for (int k = 0; k < c; k++) d[r][c] -= d[r][k] * d[c][k];
-              d[r][c] *= rs[c];
-            }
-          }
-          double y[RA][4];
-#pragma unroll
-          for (int a = 0; a < RA; a++) {
-            const int t = lane + 32 * a - j0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-              double v = raw[a][c];
-#pragma unroll
-              for (int k = 0; k < c; k++) v -= y[a][k] * d[c][k];
-              y[a][c] = (t >= c) ? v * rs[c] : 0.0;
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < RA; a++)
-            if (warp == a) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) ybuf[(lane + 32 * a) * 4 + c] = y[a][c];
-            }
-          consumerBar();
-#pragma unroll
-          for (int sl = uu; sl < CU; sl++) {
-            if (UF == CU || sl < rem) {
-              const int cb = NW * (u0 + sl);
-              const double2 lo = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4);
-              const double2 hi = *reinterpret_cast<const double2*>(ybuf + (warp + cb) * 4 + 2);
-              double yc[4] = {lo.x, lo.y, hi.x, hi.y};
-              if (sl == uu && !(h == 0 && warp >= 4)) {
-#pragma unroll
-                for (int c = 0; c < 4; c++) yc[c] = 0.0;
-              }
-#pragma unroll
-              for (int a = 0; a < RA; a++) {
-                if (j0 + 3 < 32 * a + 31 && cb <= 32 * a + 31) {  // warp uniform
-#pragma unroll
-                  for (int c = 0; c < 4; c++) reg[a][sl] -= y[a][c] * yc[c];
-                }
-              }
-            }
-          }
-          if (q >= 0 && q < 4) {
-#pragma unroll
-            for (int a = 0; a < RA; a++)
-              if (lane + 32 * a >= j0) reg[a][uu] = q == 0 ? y[a][0] : (q == 1 ? y[a][1] : (q == 2 ? y[a][2] : y[a][3]));
-          }
-        }
+        for (int k = 0; k < c; k++) L8[r][c] -= L8[r][k] * L8[c][k];
+        L8[r][c] *= rs[c];
       }
-    }
-    // columns warp + 8 (u0 .. u0 + UF - 1) are final: write them back (no reader before the closing barrier), then
-    // shift the live slots down
+    } else {  // identity column
+      rs[c] = 1.0;
+      L8[c][c] = 1.0;
 #pragma unroll
-    for (int uu = 0; uu < UF; uu++)
-#pragma unroll
-      for (int a = 0; a < RA; a++) S[(lane + 32 * a) * LDQ + warp + NW * (u0 + uu)] = reg[a][uu];
-    if (UF < CU) {
-#pragma unroll
-      for (int sl = 0; sl + UF < CU; sl++)
-        if (sl + UF < rem) {
-#pragma unroll
-          for (int a = 0; a < RA; a++) reg[a][sl] = reg[a][sl + UF];
-        }
+      for (int r = c + 1; r < 8; r++) L8[r][c] = 0.0;
     }
   }
-  consumerBar();
+  // lane -> row lane / 4, two columns
+  const int i = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+  for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+    for (int cc = 0; cc < 8; cc += 2)
+      if (ii == i && cc == c0) {
+        if (cc <= ii) D[ii * LDQ + cc] = L8[ii][cc];
+        if (cc + 1 <= ii) D[ii * LDQ + cc + 1] = L8[ii][cc + 1];
+        fac[ii * 8 + cc] = cc <= ii ? L8[ii][cc] : 0.0;
+        fac[ii * 8 + cc + 1] = cc + 1 <= ii ? L8[ii][cc + 1] : 0.0;
+      }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      if (c == lane) fac[64 + c] = rs[c];
+  }
+}
+
+// In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the valid region) by the 256 threads of the CTA,
+// blocked over 8-column panels with a one-panel lookahead:
+//   (b) thread per row: the rows below the diagonal tile are solved against its factor (from `fac`) by substitution;
+//   (c) the trailing update  S22 -= X X^T  runs on the tensor pipe, one 8 x 8 tile (K = 8: two DMMA) at a time: warp 0
+//       updates the NEXT diagonal tile first and factors it right away (factorTile8) while the warps 1..7 work through
+//       the other lower tiles - the serial pivot chain of panel p + 1 hides behind the update of panel p.
+// Two barriers per panel. (The register-resident scheme of panel2_kernel, four columns per step with all 256 threads
+// updating their slots with DFMA, measured 57 k cycles here; this blocked scheme without the lookahead 35 k.)
+// nd < 96: columns >= nd act as identity; rows >= nd with entries in columns < nd (rows below a partial last diagonal
+// block) ride along as the extra rows of a trapezoid and come out as M L^-T.
+__device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  if (warp == 0) factorTile8(S, min(8, nd), fac2, lane);
+  __syncthreads();
+#pragma unroll 1
+  for (int j0 = 0, pb = 0; j0 < nd; j0 += 8, pb ^= 1) {
+    const int e = min(8, nd - j0);
+    const int m = (TB - j0 - 8) / 8;  // tile rows of the trailing matrix
+    if (m <= 0) break;
+    const double* fac = fac2 + pb * 72;
+    // (b) rows below the diagonal tile
+    const int r = j0 + 8 + tid;
+    if (r < TB) {
+      double* xr = S + r * LDQ + j0;
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(xr + c);
+        x[c] = v.x, x[c + 1] = v.y;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (c < e) {
+          double v = x[c];
+#pragma unroll
+          for (int k = 0; k < c; k++) v -= x[k] * fac[c * 8 + k];
+          x[c] = v * fac[64 + c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(xr + c) = make_double2(x[c], x[c + 1]);
+    }
+    __syncthreads();
+    // (c) trailing update, lower tiles tt = ti (ti + 1) / 2 + tj of the m x m tile grid
+    const double* X = S + (j0 + 8) * LDQ + j0;  // panel below the diagonal tile: [8 m][8]
+    double* C = S + (j0 + 8) * LDQ + j0 + 8;
+    const int nt = m * (m + 1) / 2;
+    if (warp == 0) {
+      const double* xa = X + g * LDQ + t;
+      double c0 = 0.0, c1 = 0.0;
+      dmma(c0, c1, xa[0], xa[0]);
+      dmma(c0, c1, xa[4], xa[4]);
+      double2* cp = reinterpret_cast<double2*>(C + g * LDQ + 2 * t);
+      double2 cv = *cp;
+      cv.x -= c0, cv.y -= c1;
+      *cp = cv;
+      __syncwarp();
+      if (j0 + 8 < nd) factorTile8(C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72, lane);
+    } else {
+      // tiles 1 .. nt-1 over the warps 1 .. 7, two tiles in flight per warp
+      int tt = warp;  // first tile of this warp
+      int ti = (int)((sqrtf(8.0f * tt + 1.0f) - 1.0f) * 0.5f);
+      ti += ((ti + 1) * (ti + 2) / 2 <= tt) ? 1 : 0;
+      ti -= (ti * (ti + 1) / 2 > tt) ? 1 : 0;
+      int tj = tt - ti * (ti + 1) / 2;
+#pragma unroll 1
+      for (; tt < nt; tt += 14) {
+        int ti2 = ti, tj2 = tj + 7;
+        while (tj2 > ti2) tj2 -= ti2 + 1, ti2++;
+        const bool has2 = tt + 7 < nt;
+        const double* xa = X + (8 * ti + g) * LDQ + t;
+        const double* xb = X + (8 * tj + g) * LDQ + t;
+        const double* ya = X + (8 * (has2 ? ti2 : ti) + g) * LDQ + t;
+        const double* yb = X + (8 * (has2 ? tj2 : tj) + g) * LDQ + t;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        dmma(c0, c1, xa[0], xb[0]);
+        dmma(d0, d1, ya[0], yb[0]);
+        dmma(c0, c1, xa[4], xb[4]);
+        dmma(d0, d1, ya[4], yb[4]);
+        double2* cp = reinterpret_cast<double2*>(C + (8 * ti + g) * LDQ + 8 * tj + 2 * t);
+        double2 cv = *cp;
+        cv.x -= c0, cv.y -= c1;
+        *cp = cv;
+        if (has2) {
+          double2* dp = reinterpret_cast<double2*>(C + (8 * ti2 + g) * LDQ + 8 * tj2 + 2 * t);
+          double2 dv = *dp;
+          dv.x -= d0, dv.y -= d1;
+          *dp = dv;
+        }
+        // advance (ti, tj) by 14 tiles in the row-major lower-triangular enumeration
+        tj += 14;
+        while (tj > ti) tj -= ti + 1, ti++;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // One warp: dst(8 x 8, ldd) = sign * X(8 x K, ldx) * Y(K x 8, ldy), K a multiple of 4, all in shared memory (DMMA m8n8k4;
@@ -361,21 +388,28 @@ __device__ __forceinline__ void invertTile(const double* S, double* Wm, double* 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-// job t (column-major): t = 0 -> diagonal block 0; then for c = 0 .. nbc-1 the rows i = c+1 .. nbr-1 of block column
-// c; (c+1, c) with c+1 < nbc is the diagonal job of block c+1 (tiles (c+1,c) and (c+1,c+1)).
+// Two job streams. Diagonal job d (d = 0 .. nbc-1) owns the tiles (d, d-1) and (d, d); the first `chainCtas` CTAs to
+// arrive take them in order and do nothing else while there are any: a diagonal job accumulates 2 (d - 1) tile products
+// before it reaches the serial part of the chain, and must have started that long before the chain arrives (handed
+// out in column-major order with the regular tiles, the late diagonal jobs started late and the run ended in a tail of
+// single CTAs accumulating for ~0.9 ms). Regular job t: the remaining tiles in column-major order, rows
+// i = c+2 .. nbr-1 of block column c (i = c+1 too where there is no diagonal block c+1: rows below the lump's square).
+// A job only waits for jobs with smaller tickets of its own stream, or for jobs of the other stream that in turn only
+// depend on smaller tickets: no deadlock whatever the number of co-resident CTAs, as long as chain CTAs are the first to
+// arrive (they are resident by construction).
 struct Job {
   int i, c, diag;  // diag: this job also owns the diagonal tile (i, i)
 };
-__device__ __forceinline__ Job decodeJob(int t, int nbc, int nbr) {
+__device__ __forceinline__ int firstRegularRow(int c, int nbc) { return c + 1 < nbc ? c + 2 : c + 1; }
+__device__ __forceinline__ Job decodeRegular(int t, int nbc, int nbr) {
   Job j;
-  if (t == 0) {
-    j.i = 0, j.c = -1, j.diag = 1;
-    return j;
+  int rem = t, c = 0;
+  for (;;) {
+    const int cnt = max(0, nbr - firstRegularRow(c, nbc));
+    if (rem < cnt) break;
+    rem -= cnt, c++;
   }
-  int rem = t - 1, c = 0;
-  while (rem >= nbr - c - 1) rem -= nbr - c - 1, c++;
-  j.c = c, j.i = c + 1 + rem;
-  j.diag = (rem == 0 && c + 1 < nbc) ? 1 : 0;
+  j.c = c, j.i = firstRegularRow(c, nbc) + rem, j.diag = 0;
   return j;
 }
 
@@ -445,26 +479,29 @@ __device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int kTiles, ui
   }
 }
 
-// x(24 x 48 per warp) = M[rbase.., :] W[cbase.., :]^T for the operands staged in E0 (M, [96][LDE]) and E1 (W): W is lower
-// triangular, so column tile j only sees k < its last column + 1
-__device__ __forceinline__ void trsmProduct(double (&x)[3][6][2], const double* E0, const double* E1, int rbase, int cbase,
+// x = M[rbase .. rbase+24, :] W[cols, :]^T for the operands staged in E0 (M, [96][LDE]) and E1 (W): this warp's six 8-column
+// tiles are the INTERLEAVED tiles 2 j + wn (j < 6) of the twelve. W is lower triangular, so column tile c only sees
+// k < 8 c + 8: interleaving balances that triangular work between the two warps that share an SM sub-partition (with
+// contiguous halves the warp of the left half finishes early and the other one issues DMMA alone, at half rate:
+// 14.4 k cycles measured against 7.5 k of tensor-pipe time).
+__device__ __forceinline__ void trsmProduct(double (&x)[3][6][2], const double* E0, const double* E1, int rbase, int wn,
                                             int g, int t) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 6; j++) x[i][j][0] = x[i][j][1] = 0.0;
   const double* as = E0 + (rbase + g) * LDE + t;
-  const double* bs = E1 + (cbase + g) * LDE + t;
+  const double* bs = E1 + (8 * wn + g) * LDE + t;
 #pragma unroll 2
   for (int kk = 0; kk < TB; kk += 4) {
     double af[3], bf[6];
 #pragma unroll
     for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
 #pragma unroll
-    for (int j = 0; j < 6; j++) bf[j] = bs[j * 8 * LDE + kk];
+    for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
 #pragma unroll
     for (int j = 0; j < 6; j++)
-      if (kk < cbase + 8 * j + 8) {
+      if (kk < 8 * (2 * j + wn) + 8) {
 #pragma unroll
         for (int i = 0; i < 3; i++) dmma(x[i][j][0], x[i][j][1], af[i], bf[j]);
       }
@@ -513,12 +550,30 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   double* __restrict__ A = p.A;
   const int64_t ld = p.ld;
 
+  __shared__ int chainS;
+  if (tid == 0) chainS = (int)(atomicAdd(p.ctr + 2, 1u) - p.arriveBase) < p.chainCtas;
+  __syncthreads();
+  bool chain = chainS != 0;
+
   for (;;) {
-    if (tid == 0) jobS = (int)(atomicAdd(p.ticket, 1u) - p.ticketBase);
-    __syncthreads();
-    const int jt = jobS;
-    if (jt >= p.numJobs) break;
-    const Job job = decodeJob(jt, p.nbc, p.nbr);
+    Job job;
+    if (chain) {
+      if (tid == 0) jobS = (int)(atomicAdd(p.ctr + 3, 1u) - p.diagBase);
+      __syncthreads();
+      const int dj = jobS;
+      __syncthreads();
+      if (dj >= p.nbc) {  // the chain is finished (or about to be): help with the regular tiles
+        chain = false;
+        continue;
+      }
+      job.i = dj, job.c = dj - 1, job.diag = 1;
+    } else {
+      if (tid == 0) jobS = (int)(atomicAdd(p.ctr, 1u) - p.ticketBase);
+      __syncthreads();
+      const int jt = jobS;
+      if (jt >= p.numRegular) break;
+      job = decodeRegular(jt, p.nbc, p.nbr);
+    }
     const int c = job.c, bi = job.i;
     const int kTiles = c > 0 ? c * (TB / BK) : 0;  // K = 96 c
     const int rowA0 = bi * TB, rowB0 = (c < 0 ? 0 : c) * TB;
@@ -574,20 +629,24 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       mbarWait(wBar, wUses & 1);  // W_c has landed in E1 (requested by thread 0 right after the main loop)
       wUses++;
       double x[3][6][2];
-      trsmProduct(x, E0, E1, rbase, cbase, g, t);
+      trsmProduct(x, E0, E1, rbase, wn, g, t);
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
           const int64_t gr = (int64_t)rowA0 + r;
           if (gr < p.rows && cc < nc)
             *reinterpret_cast<double2*>(A + gr * ld + c * TB + cc) = make_double2(x[i][j][0], x[i][j][1]);
         }
-      __threadfence();
       fenceProxyAsync();
       consumerBar();
-      if (tid == 0) stRelease(p.done + (int64_t)bi * p.nbc + c, p.epoch);
+      // one fence by the releasing thread after the barrier (the pattern of a grid sync): the barrier orders the CTA's
+      // stores before it, the release is cumulative at gpu scope
+      if (tid == 0) {
+        __threadfence();
+        stRelease(p.done + (int64_t)bi * p.nbc + c, p.epoch);
+      }
       __syncthreads();  // (B)
       cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
       continue;
@@ -637,63 +696,72 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       wUses++;
       LC_STAMP(3)
       double x[3][6][2];
-      const int cbase = 48 * wn;
-      trsmProduct(x, E0, E1, rbase, cbase, g, t);
+      trsmProduct(x, E0, E1, rbase, wn, g, t);
       consumerBar();  // every read of M1 and W is done: E0 becomes L1, E1 becomes the diagonal block
       LC_STAMP(4)
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
           const double2 v = make_double2(x[i][j][0], x[i][j][1]);
           *reinterpret_cast<double2*>(E0 + r * LDE + cc) = v;
           if (rowA0 + r < p.rows) *reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc) = v;
         }
-      __threadfence();
     }
     for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
     consumerBar();
-    if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+    if (c >= 0 && tid == 0) {
+      __threadfence();
+      stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+    }
     LC_STAMP(5)
     // 3. D = P - L1 L1^T on the 78 lower tiles, spread over the eight warps (tile tt -> warp tt mod 8), straight into S
     {
-      double y[10][2];
-      int rowI[10], rowJ[10];  // tile tt = ti (ti + 1) / 2 + tj  ->  first rows of its two operands
+      // warp (wm, wn): three tile rows chosen so that every wm holds 18 - 21 lower tiles ({11,4,1}, {10,5,2}, {9,6,3},
+      // {8,7,0}), column tiles 2 j + wn: 9 fragment loads per 18 DMMA, and the two warps of an SM sub-partition
+      // (same wm) carry the same load
+      double y[3][6][2];
+      int rowT[3];
+      rowT[0] = 11 - wm, rowT[1] = wm == 3 ? 7 : 4 + wm, rowT[2] = wm == 3 ? 0 : 1 + wm;
 #pragma unroll
-      for (int q = 0; q < 10; q++) {
-        y[q][0] = y[q][1] = 0.0;
-        const int tt = min(warp + 8 * q, 77);
-        int ti = (int)((sqrtf(8.0f * tt + 1.0f) - 1.0f) * 0.5f);
-        ti += ((ti + 1) * (ti + 2) / 2 <= tt) ? 1 : 0;
-        ti -= (ti * (ti + 1) / 2 > tt) ? 1 : 0;
-        rowI[q] = 8 * ti, rowJ[q] = 8 * (tt - ti * (ti + 1) / 2);
-      }
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) y[i][j][0] = y[i][j][1] = 0.0;
       if (c >= 0) {
-#pragma unroll 1
+        const double* bs = E0 + (8 * wn + g) * LDE + t;
+#pragma unroll 2
         for (int kk = 0; kk < TB; kk += 4) {
+          double af[3], bf[6];
 #pragma unroll
-          for (int q = 0; q < 10; q++)
-            if (warp + 8 * q < 78)
-              dmma(y[q][0], y[q][1], E0[(rowI[q] + g) * LDE + kk + t], E0[(rowJ[q] + g) * LDE + kk + t]);
+          for (int i = 0; i < 3; i++) af[i] = E0[(8 * rowT[i] + g) * LDE + kk + t];
+#pragma unroll
+          for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+              if (2 * j + wn <= rowT[i]) dmma(y[i][j][0], y[i][j][1], af[i], bf[j]);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 10; q++) {
-        const int tt = warp + 8 * q;
-        if (tt < 78) {
-          const double2 pv = *reinterpret_cast<const double2*>(Pk + tt * 64 + g * 8 + 2 * t);
-          const int r = rowI[q] + g, cc = rowJ[q] + 2 * t;
-          // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along
-          // the factorization as the extra rows of a trapezoid: they come out as M L^-T
-          if (cc <= r && cc < nd && rowA0 + r < p.rows) S[r * LDQ + cc] = pv.x - y[q][0];
-          if (cc + 1 <= r && cc + 1 < nd && rowA0 + r < p.rows) S[r * LDQ + cc + 1] = pv.y - y[q][1];
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int ti = rowT[i], tj = 2 * j + wn;
+          if (tj <= ti) {
+            const double2 pv = *reinterpret_cast<const double2*>(Pk + (ti * (ti + 1) / 2 + tj) * 64 + g * 8 + 2 * t);
+            const int r = 8 * ti + g, cc = 8 * tj + 2 * t;
+            // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along
+            // the factorization as the extra rows of a trapezoid: they come out as M L^-T
+            if (cc <= r && cc < nd && rowA0 + r < p.rows) S[r * LDQ + cc] = pv.x - y[i][j][0];
+            if (cc + 1 <= r && cc + 1 < nd && rowA0 + r < p.rows) S[r * LDQ + cc + 1] = pv.y - y[i][j][1];
+          }
         }
-      }
     }
     consumerBar();
     LC_STAMP(7)
-    potrfTile<UF>(S, nd, colbuf, ybuf, warp, lane);
+    potrfTile(S, nd, colbuf, tid, warp, lane);
     LC_STAMP(8)
     if (nd < TB) {
       // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion
@@ -719,9 +787,11 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       double* __restrict__ W = p.wbuf + (int64_t)d * TB * LDE;
       for (int idx = tid; idx < TB * LDE / 2; idx += kConsumers)
         *reinterpret_cast<double2*>(W + 2 * idx) = *reinterpret_cast<const double2*>(E0 + 2 * idx);
-      __threadfence();
       consumerBar();
-      if (tid == 0) stRelease(p.wdone + d, p.epoch);
+      if (tid == 0) {
+        __threadfence();
+        stRelease(p.wdone + d, p.epoch);
+      }
       LC_STAMP(10)
     }
     // L(d,d) -> global (lower triangle, coalesced rows)
@@ -772,7 +842,7 @@ struct LcState {
   DevBuf<double> wbuf;
   int nbcCap = 0;
   int64_t tileCap = 0;
-  unsigned epoch = 0, ticketBase = 0;
+  unsigned epoch = 0, ticketBase = 0, arriveBase = 0, diagBase = 0;
 };
 long long*& lastDbg() {
   static long long* p = nullptr;
@@ -816,9 +886,10 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   LcParams p;
   p.A = A, p.ld = ld, p.n = (int)n, p.rows = (int)(n + rowsBelow);
   p.nbc = ceilDiv(n, TB), p.nbr = ceilDiv(n + rowsBelow, TB);
-  int64_t jobs = 1;
-  for (int c = 0; c < p.nbc; c++) jobs += p.nbr - c - 1;
-  p.numJobs = (int)jobs;
+  int64_t regular = 0;
+  for (int c = 0; c < p.nbc; c++) regular += std::max(0, p.nbr - (c + 1 < p.nbc ? c + 2 : c + 1));
+  p.numRegular = (int)regular;
+  const int64_t jobs = regular + p.nbc;
 
   LcState& s = lcState(st);
   const int64_t tiles = (int64_t)p.nbr * p.nbc;
@@ -826,15 +897,15 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
     B200_CUDA(cudaStreamSynchronize(st));
     s.nbcCap = std::max(p.nbc, s.nbcCap * 2);
     s.tileCap = std::max(tiles, s.tileCap * 2);
-    s.words.resize((size_t)(2 + s.nbcCap + s.tileCap));
+    s.words.resize((size_t)(4 + s.nbcCap + s.tileCap));
     s.wbuf.resize((size_t)s.nbcCap * TB * LDE);
     B200_CUDA(cudaMemsetAsync(s.words.ptr(), 0, s.words.size() * sizeof(unsigned), st));
-    s.epoch = 0, s.ticketBase = 0;
+    s.epoch = 0, s.ticketBase = s.arriveBase = s.diagBase = 0;
   }
-  p.ticket = s.words.ptr(), p.abortFlag = s.words.ptr() + 1, p.wdone = s.words.ptr() + 2;
-  p.done = s.words.ptr() + 2 + s.nbcCap;
+  p.ctr = s.words.ptr(), p.abortFlag = s.words.ptr() + 1, p.wdone = s.words.ptr() + 4;
+  p.done = s.words.ptr() + 4 + s.nbcCap;
   p.wbuf = s.wbuf.ptr();
-  p.epoch = ++s.epoch, p.ticketBase = s.ticketBase;
+  p.epoch = ++s.epoch, p.ticketBase = s.ticketBase, p.arriveBase = s.arriveBase, p.diagBase = s.diagBase;
   p.dbg = nullptr;
   if (const char* e = getenv("BSPB200_LUMPCHOL_DBG")) {
     if (atoi(e) != 0) {
@@ -864,6 +935,10 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   int64_t want = (int64_t)(1.5 * flops / (p.nbc * 40e-6 * 200e9)) + 1;
   if (const char* e = getenv("BSPB200_LUMPCHOL_GRID")) want = atoi(e);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)sms, jobs, std::max<int64_t>(want, 16)}));
+  // chain CTAs: a diagonal job needs ~0.4 chain steps of accumulation per block column it has behind it
+  int chain = std::max(1, std::min((int)(0.4 * p.nbc) + 1, std::max(1, grid / 3)));
+  if (const char* e = getenv("BSPB200_LUMPCHOL_CHAIN")) chain = std::max(1, std::min(atoi(e), grid));
+  p.chainCtas = chain;
   ProfScope prof(st, KC_LUMP_CHOL, flops, 0);
   // column slots of the diagonal-block Cholesky unrolled per loop iteration (BSPB200_LUMPCHOL_UF: 1, 2, 3, 4, 6, 12)
   const char* ufe = getenv("BSPB200_LUMPCHOL_UF");
@@ -881,7 +956,10 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
     default: launch(lump_chol_kernel<2>); break;
   }
   B200_LAUNCH_CHECK();
-  s.ticketBase += (unsigned)(jobs + grid);
+  // every CTA ends with one failing fetch of the regular ticket; the chain CTAs with one failing fetch of the diagonal one
+  s.ticketBase += (unsigned)(regular + grid);
+  s.arriveBase += (unsigned)grid;
+  s.diagBase += (unsigned)(p.nbc + std::min(chain, grid));
   return true;
 }
 

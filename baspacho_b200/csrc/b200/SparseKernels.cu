@@ -732,5 +732,147 @@ void assembleVecT(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, in
 B200_INSTANTIATE_SPARSE(double)
 B200_INSTANTIATE_SPARSE(float)
 
+
+// ---------------------------------------------------------------------------------------------------------
+// "Fragmented" whole-range ops (reference MatOps.h:168-183, CPU implementation MatOpsFast.cpp:613-1018; the reference's
+// CUDA backend has none): every lump is a single span, nRHS = 1, so the matrix is a block-CSC of small blocks and the
+// dense-lump machinery (one launch per lump) is pure overhead. Here: one warp per span, lane i owns entry i of the span
+// (spans of at most 32 scalars), every block read once per use with the lanes walking down a block column, a span's
+// row blocks gathered in a fixed order (no atomics: deterministic, unlike a scatter), triangular solves scheduled by
+// LEVELS of the block dependency graph (all spans of a level are independent; one launch per level).
+template <typename T>
+__global__ void __launch_bounds__(128) frag_mv_kernel(FragDev f, DevSkel sk, Mats<T> data, Mats<T> X, Mats<T> Y,
+                                                      int64_t spanBegin, int64_t spanEnd, T alpha) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = spanBegin + (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (s >= sk.numSpans) return;
+  const T* __restrict__ d = data.at(blockIdx.z);
+  const T* __restrict__ x = X.at(blockIdx.z);
+  T* y = Y.at(blockIdx.z);
+  const int64_t s0 = sk.spanStart[s];
+  const int sn = (int)(sk.spanStart[s + 1] - s0);
+  T acc = T(0);
+  if (s < spanEnd && lane < sn) {
+    const int64_t cp = sk.chainColPtr[s], ce = sk.chainColPtr[s + 1];
+    const T* D = d + sk.chainData[cp];  // sn x sn, lower triangle meaningful: symmetric product
+    for (int j = 0; j <= lane; j++) acc += D[lane * sn + j] * x[s0 + j];
+    for (int j = lane + 1; j < sn; j++) acc += D[j * sn + lane] * x[s0 + j];
+    for (int64_t p = cp + 1; p < ce; p++) {  // blocks below in this column: y_s += B^T x_r
+      const int64_t r = sk.chainRowSpan[p], r0 = sk.spanStart[r];
+      const int rn = (int)(sk.spanStart[r + 1] - r0);
+      const T* B = d + sk.chainData[p];  // rn x sn
+      for (int i = 0; i < rn; i++) acc += B[i * sn + lane] * x[r0 + i];
+    }
+  }
+  if (lane < sn) {
+    for (int32_t q = f.rowPtr[s]; q < f.rowPtr[s + 1]; q++) {  // blocks in this row: y_s += B x_c
+      const int32_t c = f.rowCol[q];
+      if (c < spanBegin || c >= spanEnd) continue;
+      const int64_t c0 = sk.spanStart[c];
+      const int cn = (int)(sk.spanStart[c + 1] - c0);
+      const T* B = d + f.rowOff[q];  // sn x cn
+      for (int j = 0; j < cn; j++) acc += B[lane * cn + j] * x[c0 + j];
+    }
+    y[s0 + lane] += alpha * acc;
+  }
+}
+
+// forward: spans list[0 .. count) (one level, or the rows behind the range when `diag` is false)
+template <typename T>
+__global__ void __launch_bounds__(128) frag_solve_l_kernel(FragDev f, DevSkel sk, Mats<T> data, Mats<T> Y,
+                                                           const int32_t* __restrict__ list, int count, int64_t spanBegin,
+                                                           int64_t spanEnd, bool diag) {
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (idx >= count) return;
+  const int64_t s = list[idx];
+  const T* __restrict__ d = data.at(blockIdx.z);
+  T* y = Y.at(blockIdx.z);
+  const int64_t s0 = sk.spanStart[s];
+  const int sn = (int)(sk.spanStart[s + 1] - s0);
+  T acc = lane < sn ? y[s0 + lane] : T(0);
+  if (lane < sn)
+    for (int32_t q = f.rowPtr[s]; q < f.rowPtr[s + 1]; q++) {
+      const int32_t c = f.rowCol[q];
+      if (c < spanBegin || c >= spanEnd) continue;
+      const int64_t c0 = sk.spanStart[c];
+      const int cn = (int)(sk.spanStart[c + 1] - c0);
+      const T* B = d + f.rowOff[q];
+      for (int j = 0; j < cn; j++) acc -= B[lane * cn + j] * y[c0 + j];
+    }
+  if (diag) {
+    const T* D = d + sk.chainData[sk.chainColPtr[s]];
+    for (int j = 0; j < sn; j++) {
+      const T xj = __shfl_sync(0xffffffffu, acc, j) / D[j * sn + j];
+      if (lane == j) acc = xj;
+      else if (lane > j && lane < sn) acc -= D[lane * sn + j] * xj;
+    }
+  }
+  if (lane < sn) y[s0 + lane] = acc;
+}
+
+// backward: one level of spans inside the range
+template <typename T>
+__global__ void __launch_bounds__(128) frag_solve_lt_kernel(DevSkel sk, Mats<T> data, Mats<T> Y,
+                                                            const int32_t* __restrict__ list, int count) {
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (idx >= count) return;
+  const int64_t s = list[idx];
+  const T* __restrict__ d = data.at(blockIdx.z);
+  T* y = Y.at(blockIdx.z);
+  const int64_t s0 = sk.spanStart[s];
+  const int sn = (int)(sk.spanStart[s + 1] - s0);
+  const int64_t cp = sk.chainColPtr[s], ce = sk.chainColPtr[s + 1];
+  T acc = lane < sn ? y[s0 + lane] : T(0);
+  if (lane < sn)
+    for (int64_t p = cp + 1; p < ce; p++) {
+      const int64_t r = sk.chainRowSpan[p], r0 = sk.spanStart[r];
+      const int rn = (int)(sk.spanStart[r + 1] - r0);
+      const T* B = d + sk.chainData[p];
+      for (int i = 0; i < rn; i++) acc -= B[i * sn + lane] * y[r0 + i];
+    }
+  const T* D = d + sk.chainData[cp];
+  for (int j = sn - 1; j >= 0; j--) {
+    const T xj = __shfl_sync(0xffffffffu, acc, j) / D[j * sn + j];
+    if (lane == j) acc = xj;
+    else if (lane < j) acc -= D[j * sn + lane] * xj;
+  }
+  if (lane < sn) y[s0 + lane] = acc;
+}
+
+template <typename T>
+void fragMV(cudaStream_t st, int batch, const FragDev& f, const DevSkel& sk, Mats<T> data, Mats<T> x, Mats<T> y,
+            int64_t spanBegin, int64_t spanEnd, T alpha, double bytes) {
+  const int64_t n = sk.numSpans - spanBegin;
+  if (n <= 0) return;
+  ProfScope prof(st, KC_SOLVE_DENSE, 0, bytes * batch);
+  frag_mv_kernel<T><<<dim3(ceilDiv(n, 4), 1, batch), 128, 0, st>>>(f, sk, data, x, y, spanBegin, spanEnd, alpha);
+  B200_LAUNCH_CHECK();
+}
+template <typename T>
+void fragSolveLLevel(cudaStream_t st, int batch, const FragDev& f, const DevSkel& sk, Mats<T> data, Mats<T> y,
+                     const int32_t* list, int count, int64_t spanBegin, int64_t spanEnd, bool diag) {
+  if (count <= 0) return;
+  frag_solve_l_kernel<T><<<dim3(ceilDiv(count, 4), 1, batch), 128, 0, st>>>(f, sk, data, y, list, count, spanBegin,
+                                                                            spanEnd, diag);
+  B200_LAUNCH_CHECK();
+}
+template <typename T>
+void fragSolveLtLevel(cudaStream_t st, int batch, const DevSkel& sk, Mats<T> data, Mats<T> y, const int32_t* list,
+                      int count) {
+  if (count <= 0) return;
+  frag_solve_lt_kernel<T><<<dim3(ceilDiv(count, 4), 1, batch), 128, 0, st>>>(sk, data, y, list, count);
+  B200_LAUNCH_CHECK();
+}
+#define B200_INST_FRAG(T)                                                                                              \
+  template void fragMV<T>(cudaStream_t, int, const FragDev&, const DevSkel&, Mats<T>, Mats<T>, Mats<T>, int64_t,       \
+                          int64_t, T, double);                                                                         \
+  template void fragSolveLLevel<T>(cudaStream_t, int, const FragDev&, const DevSkel&, Mats<T>, Mats<T>,                \
+                                   const int32_t*, int, int64_t, int64_t, bool);                                       \
+  template void fragSolveLtLevel<T>(cudaStream_t, int, const DevSkel&, Mats<T>, Mats<T>, const int32_t*, int);
+B200_INST_FRAG(double)
+B200_INST_FRAG(float)
+
 }  // namespace b200
 }  // namespace BaSpaCho

@@ -245,7 +245,11 @@ void Solver::internalSolveLRange(SolveCtx<T>& slvCtx, const T* matData, int64_t 
     }
     if (startLump > sparseElimRanges[r]) BASPACHO_CHECK_GE(startLump, sparseElimRanges[r + 1]);
   }
-  if (useFusedOps && slvCtx.hasFusedSolve()) {
+  // a fragmented skeleton (every lump a single span) with one right-hand side goes to the backend's fragmented ops, as
+  // in the reference (Solver.cpp:299-301), also when the backend offers a fused range solve: one launch per lump is the
+  // worst case for the latter
+  const bool fragL = sk.numSpans() == sk.numLumps() && nRHS == 1 && slvCtx.hasFragmentedOps();
+  if (useFusedOps && slvCtx.hasFusedSolve() && !fragL) {
     slvCtx.fusedSolveL(matData, startLump, upToLump, vecData, stride);
     return;
   }
@@ -278,7 +282,8 @@ void Solver::internalSolveLtRange(SolveCtx<T>& slvCtx, const T* matData, int64_t
   const auto& sk = factorSkel;
   const int64_t startLump = sk.spanToLump[startSpanIndex], upToLump = sk.spanToLump[endSpanIndex];
 
-  if (useFusedOps && slvCtx.hasFusedSolve()) {
+  const bool fragLt = sk.numSpans() == sk.numLumps() && nRHS == 1 && slvCtx.hasFragmentedOps();
+  if (useFusedOps && slvCtx.hasFusedSolve() && !fragLt) {
     for (int64_t r = (int64_t)sparseElimRanges.size() - 2; r >= 0; r--) {
       if (sparseElimRanges[r + 1] > upToLump) {
         BASPACHO_CHECK_LE(sparseElimRanges[r], upToLump);

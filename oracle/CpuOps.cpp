@@ -554,6 +554,73 @@ struct CpuSolveCtx : SolveCtx<T> {
     }
   }
 
+  // ---- "fragmented" whole-range ops of the reference's BLAS backend (MatOpsFast.cpp:613-1018; its naive backend has
+  // none, MatOps.h:168-183): used by the Solver when every lump is a single span and nRHS == 1. Restated from the
+  // sequential branches (the threaded ones compute the same sums chunk-wise).
+  bool hasFragmentedOps() override { return sym.useBlas; }
+
+  // y[spans >= spanBegin] += alpha * sym(A) x over the block columns [spanBegin, spanEnd)  (MatOpsFast.cpp:615-770)
+  void fragmentedMV(const T* data, const T* x, int64_t spanBegin, int64_t spanEnd, T* y, T alpha) override {
+    for (int64_t s = spanBegin; s < spanEnd; s++) {
+      const int64_t s0 = skel.spanStart[s], sn = skel.spanStart[s + 1] - s0, cp = skel.chainColPtr[s];
+      const T* D = data + skel.chainData[cp];  // sn x sn, lower triangle meaningful
+      for (int64_t i = 0; i < sn; i++) {
+        T acc = T(0);
+        for (int64_t j = 0; j <= i; j++) acc += D[i * sn + j] * x[s0 + j];
+        for (int64_t j = i + 1; j < sn; j++) acc += D[j * sn + i] * x[s0 + j];
+        y[s0 + i] += alpha * acc;
+      }
+      for (int64_t pp = cp + 1; pp < skel.chainColPtr[s + 1]; pp++) {
+        const int64_t r = skel.chainRowSpan[pp], r0 = skel.spanStart[r], rn = skel.spanStart[r + 1] - r0;
+        const T* B = data + skel.chainData[pp];  // rn x sn
+        for (int64_t i = 0; i < rn; i++) {
+          T acc = T(0);
+          for (int64_t j = 0; j < sn; j++) acc += B[i * sn + j] * x[s0 + j];
+          y[r0 + i] += alpha * acc;
+        }
+        for (int64_t j = 0; j < sn; j++) {
+          T acc = T(0);
+          for (int64_t i = 0; i < rn; i++) acc += B[i * sn + j] * x[r0 + i];
+          y[s0 + j] += alpha * acc;
+        }
+      }
+    }
+  }
+
+  // forward substitution over the block columns [spanBegin, spanEnd), updating every row below (MatOpsFast.cpp:772-921)
+  void fragmentedSolveL(const T* data, int64_t spanBegin, int64_t spanEnd, T* y) override {
+    for (int64_t s = spanBegin; s < spanEnd; s++) {
+      const int64_t s0 = skel.spanStart[s], sn = skel.spanStart[s + 1] - s0, cp = skel.chainColPtr[s];
+      solveColsLower(data + skel.chainData[cp], sn, y + s0, sn, 1);
+      for (int64_t pp = cp + 1; pp < skel.chainColPtr[s + 1]; pp++) {
+        const int64_t r = skel.chainRowSpan[pp], r0 = skel.spanStart[r], rn = skel.spanStart[r + 1] - r0;
+        const T* B = data + skel.chainData[pp];
+        for (int64_t i = 0; i < rn; i++) {
+          T acc = y[r0 + i];
+          for (int64_t j = 0; j < sn; j++) acc -= B[i * sn + j] * y[s0 + j];
+          y[r0 + i] = acc;
+        }
+      }
+    }
+  }
+
+  // backward substitution, block columns spanEnd-1 .. spanBegin (MatOpsFast.cpp:923-1018)
+  void fragmentedSolveLt(const T* data, int64_t spanBegin, int64_t spanEnd, T* y) override {
+    for (int64_t s = spanEnd - 1; s >= spanBegin; s--) {
+      const int64_t s0 = skel.spanStart[s], sn = skel.spanStart[s + 1] - s0, cp = skel.chainColPtr[s];
+      for (int64_t pp = cp + 1; pp < skel.chainColPtr[s + 1]; pp++) {
+        const int64_t r = skel.chainRowSpan[pp], r0 = skel.spanStart[r], rn = skel.spanStart[r + 1] - r0;
+        const T* B = data + skel.chainData[pp];
+        for (int64_t j = 0; j < sn; j++) {
+          T acc = y[s0 + j];
+          for (int64_t i = 0; i < rn; i++) acc -= B[i * sn + j] * y[r0 + i];
+          y[s0 + j] = acc;
+        }
+      }
+      solveColsLowerT(data + skel.chainData[cp], sn, y + s0, sn, 1);
+    }
+  }
+
   const CpuSymbolicCtx& sym;
   const CoalescedBlockMatrixSkel& skel;
   int nRHS;

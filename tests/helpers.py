@@ -98,3 +98,17 @@ def ulp_err(got, ref, mask=None):
     """max |got - ref| over the masked entries in units of eps * max|ref|"""
     g, r = (got, ref) if mask is None else (got[mask], ref[mask])
     return float(np.abs(g.astype(np.float64) - r.astype(np.float64)).max() / (EPS64 * np.abs(r).max()))
+
+
+def fragmented_skel(i, n=215, fill=0.03):
+    """the skeleton family of the reference's Partial.PartialFragmented* tests (PartialFactorSolveTest.cpp:522-720):
+    randomCols(215, 0.03, 57 + i) with block sizes randomVec(n, 2, 3, 47), every span its own lump, NO fill added (the
+    solves treat the data as a lower-triangular factor). Returns from_skel() keyword arguments."""
+    import scipy.sparse as sp
+    sizes, ptrs, inds = oapi().gen_pattern_arrays(GEN_RANDOM_COLS, [n, fill], 2, 3, 57 + i)
+    csr = sp.csr_matrix((np.ones(len(inds)), inds, ptrs), shape=(n, n))
+    csc = csr.tocsc()
+    csc.sort_indices()
+    span_start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return dict(span_start=span_start.tolist(), lump_to_span=list(range(n + 1)), col_ptr=csc.indptr.astype(np.int64).tolist(),
+                row_ind=csc.indices.astype(np.int64).tolist())

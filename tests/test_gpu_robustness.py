@@ -248,3 +248,49 @@ def test_partial_ranges_across_sparse_elimination_ranges(fused):
                 xr = rhs.copy()
                 o.solve(ref, xr, mode, a, b)
                 assert np.abs(x.cpu().numpy() - xr).max() <= H.TOL_SOLVE * max(1.0, np.abs(xr).max()), (mode, a, b)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fragmented_ops_match_oracle_and_dense(dtype):
+    """Partial.PartialFragmented{AddMv,SolveL,SolveLt} (reference tests/PartialFactorSolveTest.cpp:522-720) on the device:
+    skeletons whose lumps are single spans, nRHS = 1 - solveLFrom / solveLtFrom / addMvFrom run the level-scheduled block
+    kernels (fragmentedMV / SolveL / SolveLt of the backend, reference MatOpsFast.cpp:613-1018), checked against dense
+    triangular algebra on the bottom-right corner and against the CPU oracle's fragmented ops; a full-range solve and the
+    unfused per-lump sequence of the same library as a second opinion."""
+    for i in range(6):
+        sk = H.fragmented_skel(i)
+        n = len(sk["lump_to_span"]) - 1
+        nocross = (7 * i) % 150 + 51
+        g = bsp.Solver.from_skel(**sk)
+        o = H.oracle_cpu.OracleSolver.from_skel(**sk, backend=_capi.BACKEND_FAST, num_threads=2)
+        data = H.oapi().random_data_array(g.data_size, -1, 1, 9 + i, dtype=dtype)
+        g.damp(data, 0.0, 5.0)
+        d = torch_of(data)
+        Lm = np.tril(g.densify(data).astype(np.float64))
+        r0 = int(g.spanStart[nocross])
+        tol = 1e-12 if dtype == np.float64 else 2e-4
+        for j in range(2):
+            rhs = H.oapi().random_data_array(g.order, -1, 1, 49 + i + j, dtype=dtype).reshape(1, g.order)
+            for mode, mat in ((bsp.SOLVE_L, Lm[r0:, r0:]), (bsp.SOLVE_LT, Lm[r0:, r0:].T)):
+                x = torch_of(rhs)
+                g.solve(d, x, mode, nocross, n)
+                got = x.cpu().numpy()[0].astype(np.float64)
+                exp = rhs[0].astype(np.float64).copy()
+                exp[r0:] = np.linalg.solve(mat, exp[r0:])
+                assert np.linalg.norm(got - exp) / np.linalg.norm(exp) < tol
+                xr = rhs.copy()
+                o.solve(data, xr, mode, nocross, n)
+                assert np.abs(got - xr[0]).max() <= (H.TOL_SOLVE if dtype == np.float64 else 1e-4) * max(1.0, np.abs(xr).max())
+            # the whole range, fragmented vs the per-lump op sequence (set_fused(False) keeps the fragmented path: it
+            # is the reference's own dispatch; BSPB200-independent second opinion = dense algebra)
+            x = torch_of(rhs)
+            g.solve(d, x, bsp.SOLVE_LLT)
+            exp = np.linalg.solve(Lm.T, np.linalg.solve(Lm, rhs[0].astype(np.float64)))
+            assert np.linalg.norm(x.cpu().numpy()[0] - exp) / np.linalg.norm(exp) < tol * 10
+            y0 = H.oapi().random_data_array(g.order, -1, 1, 149 + i + j, dtype=dtype).reshape(1, g.order)
+            xin, y = torch_of(rhs), torch_of(y0)
+            g.add_mv_from(d, nocross, xin, y, alpha=3.5)
+            A = H.sym_from_lower(g.densify(data)).astype(np.float64)
+            exp = y0[0].astype(np.float64).copy()
+            exp[r0:] += 3.5 * (A[r0:, r0:] @ rhs[0, r0:].astype(np.float64))
+            assert np.linalg.norm(y.cpu().numpy()[0] - exp) / np.linalg.norm(exp) < tol

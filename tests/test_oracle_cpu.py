@@ -143,3 +143,50 @@ def test_oracle_elimination_row_variants(dtype, monkeypatch):
         scale = np.abs(outs[0]).max()
         assert np.abs(outs[1] - outs[2]).max() <= (1e-13 if dtype == np.float64 else 1e-5) * scale
         assert np.array_equal(outs[0], outs[1]) or np.array_equal(outs[0], outs[2])  # the dispatch ran one of them
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_fragmented_ops(dtype):
+    """Partial.PartialFragmented{AddMv,SolveL,SolveLt} (PartialFactorSolveTest.cpp:522-720): skeletons whose lumps are
+    single spans, nRHS = 1, solveLFrom / solveLtFrom / addMvFrom from a barrier span. The BLAS backend takes the
+    fragmented whole-range ops (MatOpsFast.cpp:613-1018), the naive backend the per-lump sequence; both must match dense
+    algebra on the bottom-right corner."""
+    for i in range(6):
+        sk = H.fragmented_skel(i)
+        n = len(sk["lump_to_span"]) - 1
+        nocross = (7 * i) % 150 + 51
+        for backend in BACKENDS:
+            s = H.oracle_cpu.OracleSolver.from_skel(**sk, backend=backend, num_threads=3)
+            assert s.num_lumps == s.num_spans == n
+            data = H.oapi().random_data_array(s.data_size, -1, 1, 9 + i, dtype=dtype)
+            s.damp(data, 0.0, 5.0)
+            Lm = np.tril(s.densify(data).astype(np.float64))
+            r0 = int(s.spanStart[nocross])
+            for j in range(2):
+                rhs = H.oapi().random_data_array(s.order, -1, 1, 49 + i + j, dtype=dtype).reshape(1, s.order)
+                tol = 1e-11 if dtype == np.float64 else 2e-4
+                x = rhs.copy()
+                s.solve(data, x, bsp_mode_l(), nocross, n)
+                exp = rhs[0].astype(np.float64).copy()
+                exp[r0:] = np.linalg.solve(Lm[r0:, r0:], exp[r0:])
+                assert np.linalg.norm(x[0] - exp) / np.linalg.norm(exp) < tol
+                x = rhs.copy()
+                s.solve(data, x, bsp_mode_lt(), nocross, n)
+                exp = rhs[0].astype(np.float64).copy()
+                exp[r0:] = np.linalg.solve(Lm[r0:, r0:].T, exp[r0:])
+                assert np.linalg.norm(x[0] - exp) / np.linalg.norm(exp) < tol
+                y0 = H.oapi().random_data_array(s.order, -1, 1, 149 + i + j, dtype=dtype).reshape(1, s.order)
+                y = y0.copy()
+                s.add_mv_from(data, nocross, rhs, y, alpha=3.5)
+                A = H.sym_from_lower(s.densify(data)).astype(np.float64)
+                exp = y0[0].astype(np.float64).copy()
+                exp[r0:] += 3.5 * (A[r0:, r0:] @ rhs[0, r0:].astype(np.float64))
+                assert np.linalg.norm(y[0] - exp) / np.linalg.norm(exp) < tol
+
+
+def bsp_mode_l():
+    return _capi.SOLVE_L
+
+
+def bsp_mode_lt():
+    return _capi.SOLVE_LT

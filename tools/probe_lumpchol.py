@@ -46,22 +46,22 @@ for uf in ufs:
     got = api.debug_read(1, buf.ctypes.data_as(C.c_void_p), buf.nbytes)
     os.environ["BSPB200_LUMPCHOL_DBG"] = "0"
     st_ = buf[:64 * 16].reshape(64, 16)
-    names = ["mainloop", "wait_W", "load_W", "trsm", "store_L1", "syrk", "zero_S", "D_to_S", "potrf", "invert", "W_store", "L_store"]
+    segs = [("mainloop", 0, 1), ("stage_M_P", 1, 2), ("wait_W", 2, 3), ("trsm", 3, 4), ("store_L1+zeroS", 4, 5), ("syrk+D", 5, 7),
+            ("potrf", 7, 8), ("invert", 8, 9), ("W_store", 9, 10), ("L_store", 10, 11)]
     nb = (n + 95) // 96
     rows = []
-    for d in range(1, min(nb, 64)):
+    for d in range(1, min(nb, 64) - 1):
         s = st_[d]
         if s[0] == 0:
             continue
-        dif = [int(s[i + 1] - s[i]) if s[i + 1] and s[i] else 0 for i in range(11)]
-        rows.append(dif)
+        rows.append([int(s[b_] - s[a_]) if s[b_] and s[a_] else 0 for _, a_, b_ in segs])
     rows = np.array(rows)
     print("diag jobs:", len(rows))
     print("phase (mean cycles over diag jobs):")
-    for i, nm in enumerate(names[:11]):
-        print(f"  {nm:10s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
-    chain = rows[:, 1:10].sum(axis=1)
-    print("chain after the main loop (wait_W .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
+    for i, (nm, _, _) in enumerate(segs):
+        print(f"  {nm:16s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
+    chain = rows[:, 3:9].sum(axis=1)
+    print("chain (trsm .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
     # W_d flag time differences between consecutive diag jobs = the realized chain step
     w10 = st_[1:nb, 10]
     w10 = w10[w10 > 0]
