@@ -492,23 +492,36 @@ __device__ __forceinline__ void trsmProduct(double (&x)[3][6][2], const double* 
     for (int j = 0; j < 6; j++) x[i][j][0] = x[i][j][1] = 0.0;
   const double* as = E0 + (rbase + g) * LDE + t;
   const double* bs = E1 + (8 * wn + g) * LDE + t;
-#pragma unroll 2
-  for (int kk = 0; kk < TB; kk += 4) {
-    double af[3], bf[6];
+  // Column tile j is live while kk < 16 j + 8 wn + 8. The dead tiles are skipped with a REAL branch (a switch that
+  // falls through the live ones): an `if` around an mma is compiled to a predicated DMMA, and a predicated-off DMMA
+  // still holds the tensor pipe for its 16 cycles (measured: no gain at all from the triangular structure).
+  const int kkEnd = wn ? TB : TB - 8;
+#pragma unroll 1
+  for (int kk = 0; kk < kkEnd; kk += 4) {
+    double af[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) af[i] = as[i * 8 * LDE + kk];
-#pragma unroll
-    for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
-#pragma unroll
-    for (int j = 0; j < 6; j++)
-      if (kk < 8 * (2 * j + wn) + 8) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) dmma(x[i][j][0], x[i][j][1], af[i], bf[j]);
-      }
+    const int jmin = kk < 8 * wn + 8 ? 0 : (kk - 8 * wn - 8) / 16 + 1;
+#define LC_TRSM_TILE(J)                                                        \
+  {                                                                            \
+    const double b = bs[(J) * 16 * LDE + kk];                                  \
+    dmma(x[0][J][0], x[0][J][1], af[0], b);                                    \
+    dmma(x[1][J][0], x[1][J][1], af[1], b);                                    \
+    dmma(x[2][J][0], x[2][J][1], af[2], b);                                    \
+  }
+    switch (jmin) {
+      case 0: LC_TRSM_TILE(0)
+      case 1: LC_TRSM_TILE(1)
+      case 2: LC_TRSM_TILE(2)
+      case 3: LC_TRSM_TILE(3)
+      case 4: LC_TRSM_TILE(4)
+      case 5: LC_TRSM_TILE(5)
+      default: break;
+    }
+#undef LC_TRSM_TILE
   }
 }
 
-template <int UF>
 __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_constant__ CUtensorMap tmap, LcParams p) {
   extern __shared__ __align__(1024) unsigned char smemRawLc[];
   // NO integer round trip on this pointer (e.g. to align it by hand): the compiler would lose the address space and
@@ -730,18 +743,28 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
         for (int j = 0; j < 6; j++) y[i][j][0] = y[i][j][1] = 0.0;
       if (c >= 0) {
         const double* bs = E0 + (8 * wn + g) * LDE + t;
-#pragma unroll 2
-        for (int kk = 0; kk < TB; kk += 4) {
-          double af[3], bf[6];
+        // live column tiles of row i: 2 j + wn <= rowT[i]; dead ones skipped by a real branch (see trsmProduct)
+        int nact[3];
 #pragma unroll
-          for (int i = 0; i < 3; i++) af[i] = E0[(8 * rowT[i] + g) * LDE + kk + t];
+        for (int i = 0; i < 3; i++) nact[i] = rowT[i] >= wn ? (rowT[i] - wn) / 2 + 1 : 0;
+#pragma unroll 1
+        for (int kk = 0; kk < TB; kk += 4) {
+          double bf[6];
 #pragma unroll
           for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
 #pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 6; j++)
-              if (2 * j + wn <= rowT[i]) dmma(y[i][j][0], y[i][j][1], af[i], bf[j]);
+          for (int i = 0; i < 3; i++) {
+            const double a = E0[(8 * rowT[i] + g) * LDE + kk + t];
+            switch (nact[i]) {
+              case 6: dmma(y[i][5][0], y[i][5][1], a, bf[5]);
+              case 5: dmma(y[i][4][0], y[i][4][1], a, bf[4]);
+              case 4: dmma(y[i][3][0], y[i][3][1], a, bf[3]);
+              case 3: dmma(y[i][2][0], y[i][2][1], a, bf[2]);
+              case 2: dmma(y[i][1][0], y[i][1][1], a, bf[1]);
+              case 1: dmma(y[i][0][0], y[i][0][1], a, bf[0]);
+              default: break;
+            }
+          }
         }
       }
 #pragma unroll
@@ -940,21 +963,8 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   if (const char* e = getenv("BSPB200_LUMPCHOL_CHAIN")) chain = std::max(1, std::min(atoi(e), grid));
   p.chainCtas = chain;
   ProfScope prof(st, KC_LUMP_CHOL, flops, 0);
-  // column slots of the diagonal-block Cholesky unrolled per loop iteration (BSPB200_LUMPCHOL_UF: 1, 2, 3, 4, 6, 12)
-  const char* ufe = getenv("BSPB200_LUMPCHOL_UF");
-  const int uf = ufe ? atoi(ufe) : 2;
-  auto launch = [&](auto kern) {
-    ensureDynSmem((const void*)kern, kSmemBytes);
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
-  };
-  switch (uf) {
-    case 1: launch(lump_chol_kernel<1>); break;
-    case 3: launch(lump_chol_kernel<3>); break;
-    case 4: launch(lump_chol_kernel<4>); break;
-    case 6: launch(lump_chol_kernel<6>); break;
-    case 12: launch(lump_chol_kernel<12>); break;
-    default: launch(lump_chol_kernel<2>); break;
-  }
+  ensureDynSmem((const void*)lump_chol_kernel, kSmemBytes);
+  lump_chol_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
   B200_LAUNCH_CHECK();
   // every CTA ends with one failing fetch of the regular ticket; the chain CTAs with one failing fetch of the diagonal one
   s.ticketBase += (unsigned)(regular + grid);

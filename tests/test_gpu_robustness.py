@@ -294,3 +294,28 @@ def test_fragmented_ops_match_oracle_and_dense(dtype):
             exp = y0[0].astype(np.float64).copy()
             exp[r0:] += 3.5 * (A[r0:, r0:] @ rhs[0, r0:].astype(np.float64))
             assert np.linalg.norm(y.cpu().numpy()[0] - exp) / np.linalg.norm(exp) < tol
+
+
+def test_fp32_gemm_runs_on_tensor_cores_with_fp32_class_accuracy():
+    """The fp32 GEMM of the factorization (reference cublasSgemm, MatOpsCuda.cu:568-590; fp32 instantiations
+    Solver.cpp:458-536) is a 3xTF32 tensor-core kernel (mma.sync m16n8k8 tf32, hi/lo split): its error against an fp64
+    product must be fp32-class (~1e-6 relative to |A||B|), three orders of magnitude below plain TF32 (~1e-3); checked on
+    aligned and unaligned shapes, lower-only and with beta."""
+    import torch
+    api = bsp.api()
+    torch.manual_seed(1)
+    for (m, n, k, lower, beta) in ((515, 130, 77, False, 0.0), (1024, 1024, 512, True, 1.0), (96, 64, 16, False, 0.5),
+                                   (333, 333, 1001, True, 0.0)):
+        a = torch.randn(m, k, device="cuda")
+        b = torch.randn(n, k, device="cuda")
+        c0 = torch.randn(m, n, device="cuda")
+        c = c0.clone()
+        api.check(api.dev_gemm_nt(_capi.F32, m, n, k, 1.5, a.data_ptr(), k, b.data_ptr(), k, beta, c.data_ptr(), n, int(lower), None))
+        torch.cuda.synchronize()
+        ref = 1.5 * (a.double() @ b.double().T) + beta * c0.double()
+        scale = (a.double().abs() @ b.double().abs().T).max().item()
+        err = (c.double() - ref).abs()
+        if lower:
+            err = torch.tril(err)
+            assert torch.equal(torch.triu(c, 1), torch.triu(c0, 1))  # entries above the diagonal are not touched
+        assert err.max().item() / scale < 3e-6, (m, n, k, err.max().item() / scale)

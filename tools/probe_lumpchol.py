@@ -18,7 +18,7 @@ M = torch.randn(n, n, dtype=torch.float64, device="cuda")
 A11 = M @ M.T + n * torch.eye(n, dtype=torch.float64, device="cuda")
 A = torch.cat([A11, torch.randn(rb, n, dtype=torch.float64, device="cuda")]).contiguous()
 st = torch.cuda.current_stream().cuda_stream
-ufs = os.environ.get("PROBE_UFS", "2").split(",")
+ufs = os.environ.get("PROBE_UFS", "0").split(",")
 for uf in ufs:
     os.environ["BSPB200_LUMPCHOL_UF"] = uf
     print("==== UF", uf)
