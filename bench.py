@@ -51,6 +51,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout must carry exactly ONE line, the JSON record. Libraries write there behind Python's back (NCCL prints its version
+# banner on fd 1 when the environment sets NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the whole run and the
+# record goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line). NVML in a thread
     (a query every 2 ms: the timed region of the headline workload is only tens of ms long, too short for a freshly
@@ -222,7 +245,7 @@ def run_reference(args):
                                    f"{os.path.basename(ocpu.blas_path() or 'none')} + {cores} threads"},
         "e2e": {"value": value, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measure_dgemm_peak(torch, dev):
@@ -593,7 +616,7 @@ def run_b200(args):
                            "factor_ms": c4["factor_ms"], "solve_ms": c4["solve_ms"], "items_on_rank0": c4["n_items"],
                            "steps": c4["steps"], "warmup": c4["warmup"], "residual": c4["residual"],
                            "gpu_launches": c4["launches"], "e2e": c4["e2e"], "detail": c4["detail"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -621,7 +644,7 @@ def run_ref_cuda(args):
             "detail": {"backend": "restated reference MatOpsCuda.cu: cusolverDnDpotrf + cublasDtrsm/Dgemm per lump, "
                                   "thread-per-pair elimination with fp64 atomics, per-lump synchronous span-table copy",
                        "legs": legs}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -636,6 +659,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
