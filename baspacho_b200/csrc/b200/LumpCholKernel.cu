@@ -151,53 +151,48 @@ __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, u
 }
 
 // ------------------------------------------------------------------------------------------------ diagonal block
-// 8 x 8 diagonal tile at D (row stride LDQ): every lane of the calling warp factors it redundantly in registers (36
-// broadcast loads; the eight dependent rsqrt of the pivots are the serial part of the whole factorization), the tile goes
-// back in place and the factor (row-major, 8 x 8) + the reciprocal pivots go to `fac` ([64 + 8]) for the panel solves.
-// e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
-__device__ __forceinline__ void factorTile8(double* D, int e, double* fac, int lane) {
-  double L8[8][8], rs[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int c = 0; c <= i; c++) L8[i][c] = D[i * LDQ + c];
+// 8 x 8 diagonal tile, factored by ONE warp with the tile spread over its lanes in the DMMA accumulator layout: lane
+// (g, t) holds the entries (g, 2t) and (g, 2t+1) in v0 / v1 - exactly what the trailing-update DMMA leaves in the
+// registers, so the tile goes from the update into the factorization without touching shared memory. Right-looking; per
+// column: the pivot is broadcast by a shuffle, every lane takes its rsqrt, the owners scale the column, three shuffles
+// hand every lane the two column entries its rank-1 update needs. The serial chain per column is
+// shuffle -> rsqrt -> scale -> shuffle -> FMA (~200 cycles); the same factorization with every lane holding the whole tile
+// in registers measured 2.2 k cycles per tile (the 110 independent updates of a tile compete with the chain for the
+// issue slots of the one warp).
+// The tile goes back to D (row stride LDQ) and the factor (row-major 8 x 8) + the reciprocal pivots to `fac` ([64 + 8])
+// for the panel solves. e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
+__device__ __forceinline__ void factorTile8(double v0, double v1, double* D, int e, double* fac, int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int c = 0; c < 8; c++) {
+    const int owner = c >> 1;  // lanes t == owner hold column c, in v0 (c even) or v1 (c odd)
     if (c < e) {
-#pragma unroll
-      for (int k = 0; k < c; k++) L8[c][c] -= L8[c][k] * L8[c][k];
-      rs[c] = rsqrtNewton(L8[c][c]);
-      L8[c][c] *= rs[c];
-#pragma unroll
-      for (int r = c + 1; r < 8; r++) {
-#pragma unroll
-        for (int k = 0; k < c; k++) L8[r][c] -= L8[r][k] * L8[c][k];
-        L8[r][c] *= rs[c];
+      const double piv = __shfl_sync(0xffffffffu, (c & 1) ? v1 : v0, 4 * c + owner);
+      const double rs = rsqrtNewton(piv);
+      if (t == owner) {
+        if (c & 1) v1 *= rs;
+        else v0 *= rs;
       }
+      if (lane == 0) fac[64 + c] = rs;
+      const double col = (c & 1) ? v1 : v0;  // meaningful on the owner lanes
+      const double a = __shfl_sync(0xffffffffu, col, 4 * g + owner);             // L[g][c]
+      const double b0 = __shfl_sync(0xffffffffu, col, 4 * (2 * t) + owner);      // L[2t][c]
+      const double b1 = __shfl_sync(0xffffffffu, col, 4 * (2 * t + 1) + owner);  // L[2t+1][c]
+      if (2 * t > c) v0 -= a * b0;
+      if (2 * t + 1 > c) v1 -= a * b1;
     } else {  // identity column
-      rs[c] = 1.0;
-      L8[c][c] = 1.0;
-#pragma unroll
-      for (int r = c + 1; r < 8; r++) L8[r][c] = 0.0;
+      if (lane == 0) fac[64 + c] = 1.0;
+      if (t == owner) {
+        if (c & 1) v1 = (g == c) ? 1.0 : 0.0;
+        else v0 = (g == c) ? 1.0 : 0.0;
+      }
     }
   }
-  // lane -> row lane / 4, two columns
-  const int i = lane >> 2, c0 = (lane & 3) * 2;
-#pragma unroll
-  for (int ii = 0; ii < 8; ii++)
-#pragma unroll
-    for (int cc = 0; cc < 8; cc += 2)
-      if (ii == i && cc == c0) {
-        if (cc <= ii) D[ii * LDQ + cc] = L8[ii][cc];
-        if (cc + 1 <= ii) D[ii * LDQ + cc + 1] = L8[ii][cc + 1];
-        fac[ii * 8 + cc] = cc <= ii ? L8[ii][cc] : 0.0;
-        fac[ii * 8 + cc + 1] = cc + 1 <= ii ? L8[ii][cc + 1] : 0.0;
-      }
-  if (lane < 8) {
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-      if (c == lane) fac[64 + c] = rs[c];
-  }
+  const int c0 = 2 * t;
+  if (c0 <= g) D[g * LDQ + c0] = v0;
+  if (c0 + 1 <= g) D[g * LDQ + c0 + 1] = v1;
+  fac[g * 8 + c0] = c0 <= g ? v0 : 0.0;
+  fac[g * 8 + c0 + 1] = c0 + 1 <= g ? v1 : 0.0;
 }
 
 // In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the valid region) by the 256 threads of the CTA,
@@ -210,9 +205,13 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* fac, int l
 // updating their slots with DFMA, measured 57 k cycles here; this blocked scheme without the lookahead 35 k.)
 // nd < 96: columns >= nd act as identity; rows >= nd with entries in columns < nd (rows below a partial last diagonal
 // block) ride along as the extra rows of a trapezoid and come out as M L^-T.
-__device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane) {
+__device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane,
+                                          long long* dbgp = nullptr /* diagnostics: 16 stamps of the first two panels */) {
   const int g = lane >> 2, t = lane & 3;
-  if (warp == 0) factorTile8(S, min(8, nd), fac2, lane);
+  if (warp == 0) {
+    const double2 v = *reinterpret_cast<const double2*>(S + g * LDQ + 2 * t);
+    factorTile8(v.x, v.y, S, min(8, nd), fac2, lane);
+  }
   __syncthreads();
 #pragma unroll 1
   for (int j0 = 0, pb = 0; j0 < nd; j0 += 8, pb ^= 1) {
@@ -220,6 +219,9 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
     const int m = (TB - j0 - 8) / 8;  // tile rows of the trailing matrix
     if (m <= 0) break;
     const double* fac = fac2 + pb * 72;
+#define LC_PSTAMP(i) \
+  if (dbgp && tid == 0 && j0 < 16) dbgp[(j0 >> 3) * 8 + (i)] = clock64();
+    LC_PSTAMP(0)
     // (b) rows below the diagonal tile
     const int r = j0 + 8 + tid;
     if (r < TB) {
@@ -242,7 +244,9 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
 #pragma unroll
       for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(xr + c) = make_double2(x[c], x[c + 1]);
     }
+    LC_PSTAMP(1)
     __syncthreads();
+    LC_PSTAMP(2)
     // (c) trailing update, lower tiles tt = ti (ti + 1) / 2 + tj of the m x m tile grid
     const double* X = S + (j0 + 8) * LDQ + j0;  // panel below the diagonal tile: [8 m][8]
     double* C = S + (j0 + 8) * LDQ + j0 + 8;
@@ -255,9 +259,10 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
       double2* cp = reinterpret_cast<double2*>(C + g * LDQ + 2 * t);
       double2 cv = *cp;
       cv.x -= c0, cv.y -= c1;
-      *cp = cv;
-      __syncwarp();
-      if (j0 + 8 < nd) factorTile8(C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72, lane);
+      LC_PSTAMP(3)
+      if (j0 + 8 < nd) factorTile8(cv.x, cv.y, C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72, lane);
+      else *cp = cv;
+      LC_PSTAMP(4)
     } else {
       // tiles 1 .. nt-1 over the warps 1 .. 7, two tiles in flight per warp
       int tt = warp;  // first tile of this warp
@@ -295,6 +300,8 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
       }
     }
     __syncthreads();
+    LC_PSTAMP(5)
+#undef LC_PSTAMP
   }
 }
 
@@ -593,6 +600,16 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
 
     const long long tJob = clock64();
     LC_STAMP(0)
+    if (c >= 0 || job.diag) {
+      // the tiles' own (original) entries are only needed after the K loop: pull them into L2 now, one 128-byte line
+      // per request, so that the epilogue does not wait for HBM (diagonal jobs measured ~10 us there, on the chain)
+      const int cols0 = (c >= 0 ? c : 0) * TB, nlines = job.diag ? 2 * TB * 6 : TB * 6;
+      for (int idx = tid; idx < nlines; idx += kConsumers) {
+        const int r = (idx / 6) % TB, l = idx % 6, second = idx / (TB * 6);
+        const int64_t gr = (int64_t)rowA0 + r, gc = (int64_t)(second ? bi * TB : cols0) + l * 16;
+        if (gr < p.rows && gc < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + gr * ld + gc));
+      }
+    }
     double acc[3][12][2];
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -613,9 +630,14 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     LC_STAMP(1)
 
     const int nc = c >= 0 ? min(TB, p.n - c * TB) : 0;  // valid columns of block column c
-    if (tid == 0 && c >= 0) {
-      // W_c -> E1 by one bulk copy (the buffer holds the padded operand layout), in flight while M is staged
+    // W_c -> E1 by one bulk copy (the buffer holds the padded operand layout). Requested right away when W_c is already
+    // published - the copy then runs under the staging below - else after the staging: a thread that spins on the flag
+    // first would hold back its share of the staging, which for a diagonal job sits on the chain.
+    bool wIssued = false;
+    auto requestW = [&](bool block) {
+      if (wIssued || c < 0) return;
       if (*(volatile unsigned*)p.abortFlag != p.epoch) {
+        if (!block && ldAcquire(p.wdone + c) != p.epoch) return;
         const long long t0 = clock64();
         waitFlag(p.wdone + c, p.epoch, p.abortFlag);
         cycWait += clock64() - t0;
@@ -623,21 +645,34 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       fenceProxyAsync();
       mbarArriveExpectTx(wBar, TB * LDE * 8);
       bulkLoad(smemU32(E1), p.wbuf + (int64_t)c * TB * LDE, TB * LDE * 8, wBar);
-    }
-
+      wIssued = true;
+    };
+    if (tid == 0) requestW(false);
     if (!job.diag) {
       // ---- regular tile: M = A(i,c) - acc -> E0 ; W_c -> E1 ; X = M W^T -> global
       const int rbase = 24 * wm, cbase = 48 * wn;
+      // every load of the tile's own entries is issued before the first use (one L2 round trip instead of eighteen)
+      {
+        double2 av[3][6];
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
-          const int64_t gr = (int64_t)rowA0 + r;
-          double2 a = make_double2(0.0, 0.0);
-          if (gr < p.rows && cc < nc) a = *reinterpret_cast<const double2*>(A + gr * ld + c * TB + cc);
-          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
-        }
+          for (int j = 0; j < 6; j++) {
+            const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+            const int64_t gr = (int64_t)rowA0 + r;
+            av[i][j] = make_double2(0.0, 0.0);
+            if (gr < p.rows && cc < nc) av[i][j] = __ldcg(reinterpret_cast<const double2*>(A + gr * ld + c * TB + cc));
+          }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+            *reinterpret_cast<double2*>(E0 + r * LDE + cc) =
+                make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]);
+          }
+      }
+      if (tid == 0) requestW(true);
       consumerBar();
       mbarWait(wBar, wUses & 1);  // W_c has landed in E1 (requested by thread 0 right after the main loop)
       wUses++;
@@ -676,32 +711,41 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     if (wn == 0) {
       if (c >= 0) {
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++) {  // twelve loads in flight per round trip
+          double2 av[12];
+          const int r = rbase + 8 * i + g;
 #pragma unroll
           for (int j = 0; j < 12; j++) {
-            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
-            double2 a = make_double2(0.0, 0.0);
-            if (rowA0 + r < p.rows) a = *reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc);
-            *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
+            av[j] = make_double2(0.0, 0.0);
+            if (rowA0 + r < p.rows)
+              av[j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + 8 * j + 2 * t));
           }
+#pragma unroll
+          for (int j = 0; j < 12; j++)
+            *reinterpret_cast<double2*>(E0 + r * LDE + 8 * j + 2 * t) =
+                make_double2(av[j].x - acc[i][j][0], av[j].y - acc[i][j][1]);
+        }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+      for (int i = 0; i < 3; i++) {
+        const int ti = 3 * wm + i, r = rbase + 8 * i + g;
+        double2 av[12];
 #pragma unroll
-        for (int j = 0; j < 12; j++) {
-          const int ti = 3 * wm + i;
-          if (j <= ti) {  // lower tiles only (warp uniform)
-            const int r = rbase + 8 * i + g, cc = 8 * j + 2 * t;
-            double2 a = make_double2(0.0, 0.0);
-            if (cc < nd && rowA0 + r < p.rows)
-              a = *reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc);
-            *reinterpret_cast<double2*>(Pk + (ti * (ti + 1) / 2 + j) * 64 + g * 8 + 2 * t) =
-                make_double2(a.x - acc[i][j][0], a.y - acc[i][j][1]);
-          }
+        for (int j = 0; j < 12; j++) {  // lower tiles only (warp uniform)
+          av[j] = make_double2(0.0, 0.0);
+          if (j <= ti && 8 * j + 2 * t < nd && rowA0 + r < p.rows)
+            av[j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)d * TB + 8 * j + 2 * t));
         }
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+          if (j <= ti)
+            *reinterpret_cast<double2*>(Pk + (ti * (ti + 1) / 2 + j) * 64 + g * 8 + 2 * t) =
+                make_double2(av[j].x - acc[i][j][0], av[j].y - acc[i][j][1]);
+      }
     }
     LC_STAMP(2)
+    if (tid == 0) requestW(true);
     consumerBar();
     if (c >= 0) {
       // 2. L1 = L(d,d-1) = M1 W^T by all eight warps (24 x 48 each)
@@ -784,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     }
     consumerBar();
     LC_STAMP(7)
-    potrfTile(S, nd, colbuf, tid, warp, lane);
+    potrfTile(S, nd, colbuf, tid, warp, lane, (p.dbg && d == 20) ? p.dbg + 63 * 16 : nullptr);
     LC_STAMP(8)
     if (nd < TB) {
       // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion

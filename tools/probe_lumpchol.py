@@ -66,6 +66,9 @@ for uf in ufs:
     w10 = st_[1:nb, 10]
     w10 = w10[w10 > 0]
     print("W flag to W flag (cycles): mean", np.diff(w10).mean(), "=", np.diff(w10).mean() / 1.965e3, "us per block column")
+    ps = st_[63]
+    print("potrf panel stamps (d = 20), panel 0:", [int(ps[i + 1] - ps[i]) for i in range(5)], "panel 1:", [int(ps[8 + i + 1] - ps[8 + i]) for i in range(5)],
+          " [solve rows, barrier, warp-0 tile update, factor 8x8, barrier]")
     cta = buf[64 * 16:].reshape(1024, 4)
     cta = cta[cta[:, 3] > 0]
     print("CTAs:", len(cta), "jobs/CTA mean", cta[:, 3].mean(), "main loop cycles mean", cta[:, 0].mean(), "epilogue cycles mean", cta[:, 1].mean(), "flag-wait cycles mean", cta[:, 2].mean(),
