@@ -217,6 +217,88 @@ __global__ void __launch_bounds__(LANES > 32 ? LANES : 128)
   }
 }
 
+// Warp-cooperative variant of the fixed-shape gather (round 2). One WARP owns a destination (or, for the heavy ones, a
+// contiguous slice of its tasks) and walks its pair tasks in order; for every task the two operand blocks are fetched
+// COALESCED - lane i < NR*K reads word i of the B block, lane i < NC*K word i of the A block: two or three 32-byte sectors
+// per block instead of one sector access per lane and word (the per-lane kernel above needs 36 sector accesses per
+// task, ncu: 12.8 sectors per request, L1 sector throughput is its bound) - and the products are formed by exchanging
+// the words with shuffles: lane (r, c0) computes the NCO = NR*NC / lanes outputs (r, c0 + j * CG) of its row, K shuffles
+// for its B row + NCO * K for the A rows. The offsets of 32 tasks are read with one coalesced load per array and handed
+// round by shuffle; four tasks are in flight per warp. Summation order per output: task order - deterministic, no
+// atomics. Heavy destinations: the CTA's warps take consecutive slices of the task list, partial sums meet in shared
+// memory and are added in warp order.
+template <typename T, int NR, int NC, int K, int NCO, bool HEAVY>
+__global__ void __launch_bounds__(HEAVY ? 256 : 128)
+    elim_gather_warp_kernel(DevElimPlan p, Mats<T> mats, const int32_t* __restrict__ list, int64_t count) {
+  static_assert(NC % NCO == 0, "outputs per lane must divide the columns");
+  constexpr int CG = NC / NCO;      // column groups: lane (r, c0) owns columns c0 + j * CG
+  constexpr int OL = NR * CG;       // lanes that own outputs
+  static_assert(OL <= 32 && NR * K <= 32 && NC * K <= 32, "shape too large for one warp");
+  constexpr int U = 4;              // tasks in flight
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int WPB = HEAVY ? 8 : 4;
+  const int64_t slot = HEAVY ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * WPB + warp;
+  if (slot >= count) return;
+  const int64_t d = list[slot];
+  T* data = mats.at(blockIdx.z);
+  int tBegin = p.dstTaskPtr[d], tEnd = p.dstTaskPtr[d + 1];
+  if (HEAVY) {  // this warp's slice of the tasks
+    const int per = (tEnd - tBegin + WPB - 1) / WPB;
+    tBegin = min(tEnd, tBegin + warp * per);
+    tEnd = min(tEnd, tBegin + per);
+  }
+  const int r = lane / CG, c0 = lane % CG;  // meaningful for lane < OL
+  T acc[NCO];
+#pragma unroll
+  for (int j = 0; j < NCO; j++) acc[j] = T(0);
+  for (int base = tBegin; base < tEnd; base += 32) {
+    const int n = min(32, tEnd - base);
+    uint32_t offA = 0, offB = 0;
+    if (lane < n) offA = p.taskA[base + lane], offB = p.taskB[base + lane];
+    for (int i = 0; i < n; i += U) {
+      T av[U], bv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t oa = __shfl_sync(0xffffffffu, offA, (i + u) & 31), ob = __shfl_sync(0xffffffffu, offB, (i + u) & 31);
+        const bool on = i + u < n;
+        av[u] = (on && lane < NC * K) ? data[oa + lane] : T(0);
+        bv[u] = (on && lane < NR * K) ? data[ob + lane] : T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        T b[K];
+#pragma unroll
+        for (int q = 0; q < K; q++) b[q] = __shfl_sync(0xffffffffu, bv[u], (r * K + q) & 31);
+#pragma unroll
+        for (int j = 0; j < NCO; j++)
+#pragma unroll
+          for (int q = 0; q < K; q++) acc[j] += b[q] * __shfl_sync(0xffffffffu, av[u], ((c0 + j * CG) * K + q) & 31);
+      }
+    }
+  }
+  T* dst = data + p.dstOff[d];
+  const int64_t stride = p.dstStride[d];
+  if constexpr (HEAVY) {
+    __shared__ T red[WPB][OL * NCO];
+    if (lane < OL)
+#pragma unroll
+      for (int j = 0; j < NCO; j++) red[warp][lane * NCO + j] = acc[j];
+    __syncthreads();
+    if (warp == 0 && lane < OL) {
+#pragma unroll
+      for (int j = 0; j < NCO; j++) {
+        T tot = T(0);
+#pragma unroll
+        for (int w = 0; w < WPB; w++) tot += red[w][lane * NCO + j];
+        dst[r * stride + c0 + j * CG] -= tot;
+      }
+    }
+  } else if (lane < OL) {
+#pragma unroll
+    for (int j = 0; j < NCO; j++) dst[r * stride + c0 + j * CG] -= acc[j];
+  }
+}
+
 // Staged variant of the fixed-shape gather. Same task ownership and summation order as elim_gather_fixed_kernel (lane
 // `sub` of a destination takes tasks sub, sub + LANES, ...; butterfly over the lanes; one read-modify-write of the
 // target), but the operand blocks reach the lanes through shared memory: a lane reading its own two blocks with
@@ -594,7 +676,8 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // for the heavy list. BSPB200_GATHER=0: direct everywhere, 2: staged everywhere. (A third variant - cooperative
   // coalesced ld.global into registers, then the stage - was measured slower on both workloads, BAL 1.92 ms and
   // stress 3.4 ms, and was removed: profiles/README.md.)
-  static const int mode = getenv("BSPB200_GATHER") ? atoi(getenv("BSPB200_GATHER")) : 1;
+  const char* modeEnv = getenv("BSPB200_GATHER");  // read at every call: tests and probes compare the variants
+  const int mode = modeEnv ? atoi(modeEnv) : 3;
   auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
     ensureDynSmem((const void*)light, smem);
     ensureDynSmem((const void*)heavy, smem);
@@ -611,6 +694,23 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
       B200_LAUNCH_CHECK();
     }
   };
+  // BSPB200_GATHER=3 (default since round 2): the warp-cooperative kernel (coalesced block loads + shuffle exchange)
+  auto warpCoop = [&](auto light, auto heavy) {
+    if (plan.numLight > 0) {
+      light<<<dim3(ceilDiv(plan.numLight, 4), 1, batch), 128, 0, st>>>(plan, data, plan.lightList, plan.numLight);
+      B200_LAUNCH_CHECK();
+    }
+    if (plan.numHeavy > 0) {
+      heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), 256, 0, st>>>(plan, data, plan.heavyList, plan.numHeavy);
+      B200_LAUNCH_CHECK();
+    }
+  };
+  if (mode == 3) {
+    if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3)
+      return warpCoop(elim_gather_warp_kernel<T, 6, 6, 3, 2, false>, elim_gather_warp_kernel<T, 6, 6, 3, 2, true>);
+    if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
+      return warpCoop(elim_gather_warp_kernel<T, 3, 3, 3, 1, false>, elim_gather_warp_kernel<T, 3, 3, 3, 1, true>);
+  }
   const bool staged = mode != 0;
   if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
     if (staged)
