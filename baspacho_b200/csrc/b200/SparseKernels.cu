@@ -677,7 +677,10 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // coalesced ld.global into registers, then the stage - was measured slower on both workloads, BAL 1.92 ms and
   // stress 3.4 ms, and was removed: profiles/README.md.)
   const char* modeEnv = getenv("BSPB200_GATHER");  // read at every call: tests and probes compare the variants
-  const int mode = modeEnv ? atoi(modeEnv) : 3;
+  // default 1 (per-lane gather, staged heavy list). Mode 3 (warp-per-destination, coalesced loads + shuffle exchange) is
+  // kept as a measured negative: BAL 1.71 vs 1.43 ms, stress 3.80 vs 2.31 ms for the whole elimination (7x the
+  // instructions per task); a quad-transposed load variant measured 2.1 ms for the BAL gather and was dropped.
+  const int mode = modeEnv ? atoi(modeEnv) : 1;
   auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
     ensureDynSmem((const void*)light, smem);
     ensureDynSmem((const void*)heavy, smem);
@@ -694,7 +697,7 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
       B200_LAUNCH_CHECK();
     }
   };
-  // BSPB200_GATHER=3 (default since round 2): the warp-cooperative kernel (coalesced block loads + shuffle exchange)
+  // BSPB200_GATHER=3 (opt-in): the warp-cooperative kernel (coalesced block loads + shuffle exchange)
   auto warpCoop = [&](auto light, auto heavy) {
     if (plan.numLight > 0) {
       light<<<dim3(ceilDiv(plan.numLight, 4), 1, batch), 128, 0, st>>>(plan, data, plan.lightList, plan.numLight);
