@@ -112,6 +112,12 @@ __device__ __forceinline__ void bulkLoad(uint32_t dst, const void* src, int byte
                : "memory");
 }
 __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared -> global bulk copy (async proxy, bulk-group completion): the issuing thread commits and later waits
+__device__ __forceinline__ void bulkStore(void* dst, uint32_t src, int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ unsigned ldAcquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -159,40 +165,47 @@ __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, u
 // shuffle -> rsqrt -> scale -> shuffle -> FMA (~200 cycles); the same factorization with every lane holding the whole tile
 // in registers measured 2.2 k cycles per tile (the 110 independent updates of a tile compete with the chain for the
 // issue slots of the one warp).
-// The tile goes back to D (row stride LDQ) and the factor (row-major 8 x 8) + the reciprocal pivots to `fac` ([64 + 8])
-// for the panel solves. e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
-__device__ __forceinline__ void factorTile8(double v0, double v1, double* D, int e, double* fac, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+// The tile is factored in place in D (row stride LDQ, lower triangle) and the reciprocal pivots go to rsOut[8] for the
+// panel solves. Round 2c: the 32 lanes all run the whole 8 x 8 factorization redundantly on their own copy (the
+// lane-distributed version spent 2.2 k cycles per tile in the shuffles of its 8 pivot steps; the warp has nothing
+// else to do there). e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
+__device__ __forceinline__ void factorTile8(double* D, int e, double* rsOut, int lane) {
+  // every lane holds the whole lower triangle (broadcast loads, static register indices): no shuffle on the pivot chain
+  double a[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int c = 0; c <= (r | 1); c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(D + r * LDQ + c);
+      a[r][c] = v.x, a[r][c + 1] = v.y;
+    }
+  double rs[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    const int owner = c >> 1;  // lanes t == owner hold column c, in v0 (c even) or v1 (c odd)
     if (c < e) {
-      const double piv = __shfl_sync(0xffffffffu, (c & 1) ? v1 : v0, 4 * c + owner);
-      const double rs = rsqrtNewton(piv);
-      if (t == owner) {
-        if (c & 1) v1 *= rs;
-        else v0 *= rs;
-      }
-      if (lane == 0) fac[64 + c] = rs;
-      const double col = (c & 1) ? v1 : v0;  // meaningful on the owner lanes
-      const double a = __shfl_sync(0xffffffffu, col, 4 * g + owner);             // L[g][c]
-      const double b0 = __shfl_sync(0xffffffffu, col, 4 * (2 * t) + owner);      // L[2t][c]
-      const double b1 = __shfl_sync(0xffffffffu, col, 4 * (2 * t + 1) + owner);  // L[2t+1][c]
-      if (2 * t > c) v0 -= a * b0;
-      if (2 * t + 1 > c) v1 -= a * b1;
+      rs[c] = rsqrtNewton(a[c][c]);
+#pragma unroll
+      for (int r = c; r < 8; r++) a[r][c] *= rs[c];
+#pragma unroll
+      for (int j = c + 1; j < 8; j++)
+#pragma unroll
+        for (int r = j; r < 8; r++) a[r][j] -= a[r][c] * a[j][c];
     } else {  // identity column
-      if (lane == 0) fac[64 + c] = 1.0;
-      if (t == owner) {
-        if (c & 1) v1 = (g == c) ? 1.0 : 0.0;
-        else v0 = (g == c) ? 1.0 : 0.0;
-      }
+      rs[c] = 1.0;
+#pragma unroll
+      for (int r = c; r < 8; r++) a[r][c] = (r == c) ? 1.0 : 0.0;
     }
   }
-  const int c0 = 2 * t;
-  if (c0 <= g) D[g * LDQ + c0] = v0;
-  if (c0 + 1 <= g) D[g * LDQ + c0 + 1] = v1;
-  fac[g * 8 + c0] = c0 <= g ? v0 : 0.0;
-  fac[g * 8 + c0 + 1] = c0 + 1 <= g ? v1 : 0.0;
+  // lane 0 writes the tile back (one predicate for straight-line vector stores: a store per lane-and-entry predicate
+  // compiled into a divergent jump table, 10 k cycles). The entry right of the diagonal of an even row rides along.
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c <= (r | 1); c += 2) *reinterpret_cast<double2*>(D + r * LDQ + c) = make_double2(a[r][c], a[r][c + 1]);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(rsOut + c) = make_double2(rs[c], rs[c + 1]);
+  }
 }
 
 // In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the valid region) by the 256 threads of the CTA,
@@ -208,10 +221,7 @@ __device__ __forceinline__ void factorTile8(double v0, double v1, double* D, int
 __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane,
                                           long long* dbgp = nullptr /* diagnostics: 16 stamps of the first two panels */) {
   const int g = lane >> 2, t = lane & 3;
-  if (warp == 0) {
-    const double2 v = *reinterpret_cast<const double2*>(S + g * LDQ + 2 * t);
-    factorTile8(v.x, v.y, S, min(8, nd), fac2, lane);
-  }
+  if (warp == 0) factorTile8(S, min(8, nd), fac2 + 64, lane);
   __syncthreads();
 #pragma unroll 1
   for (int j0 = 0, pb = 0; j0 < nd; j0 += 8, pb ^= 1) {
@@ -222,9 +232,10 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
 #define LC_PSTAMP(i) \
   if (dbgp && tid == 0 && j0 < 16) dbgp[(j0 >> 3) * 8 + (i)] = clock64();
     LC_PSTAMP(0)
-    // (b) rows below the diagonal tile
+    // (b) rows below the diagonal tile: right-looking substitution (two dependent operations per column)
     const int r = j0 + 8 + tid;
     if (r < TB) {
+      const double* Dt = S + j0 * LDQ + j0;  // the factored diagonal tile (broadcast reads)
       double* xr = S + r * LDQ + j0;
       double x[8];
 #pragma unroll
@@ -232,13 +243,21 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
         const double2 v = *reinterpret_cast<const double2*>(xr + c);
         x[c] = v.x, x[c + 1] = v.y;
       }
+      double Lt[8][8];
+#pragma unroll
+      for (int j = 1; j < 8; j++)
+#pragma unroll
+        for (int c = 0; c < j; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(Dt + j * LDQ + c);
+          Lt[j][c] = v.x, Lt[j][c + 1] = v.y;
+        }
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         if (c < e) {
-          double v = x[c];
+          x[c] *= fac[64 + c];
 #pragma unroll
-          for (int k = 0; k < c; k++) v -= x[k] * fac[c * 8 + k];
-          x[c] = v * fac[64 + c];
+          for (int j = c + 1; j < 8; j++)
+            if (j < e) x[j] -= x[c] * Lt[j][c];
         }
       }
 #pragma unroll
@@ -260,21 +279,27 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
       double2 cv = *cp;
       cv.x -= c0, cv.y -= c1;
       LC_PSTAMP(3)
-      if (j0 + 8 < nd) factorTile8(cv.x, cv.y, C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72, lane);
-      else *cp = cv;
+      *cp = cv;
+      if (j0 + 8 < nd) {
+        __syncwarp();
+        factorTile8(C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72 + 64, lane);
+      }
       LC_PSTAMP(4)
-    } else {
-      // tiles 1 .. nt-1 over the warps 1 .. 7, two tiles in flight per warp
-      int tt = warp;  // first tile of this warp
+    } else if (warp != 4) {
+      // tiles 1 .. nt-1 over the warps 1, 2, 3, 5, 6, 7, two tiles in flight per warp. Warp 4 sits out: it shares the SM
+      // sub-partition - and with it the fp64 / DMMA pipe - with warp 0, whose serial pivot chain is the critical path of
+      // the panel (with warp 4 issuing DMMA the 8 x 8 factorization measured 10 k cycles instead of < 1 k)
+      const int wslot = warp < 4 ? warp - 1 : warp - 2;  // 0 .. 5
+      int tt = 1 + wslot;  // first tile of this warp
       int ti = (int)((sqrtf(8.0f * tt + 1.0f) - 1.0f) * 0.5f);
       ti += ((ti + 1) * (ti + 2) / 2 <= tt) ? 1 : 0;
       ti -= (ti * (ti + 1) / 2 > tt) ? 1 : 0;
       int tj = tt - ti * (ti + 1) / 2;
 #pragma unroll 1
-      for (; tt < nt; tt += 14) {
-        int ti2 = ti, tj2 = tj + 7;
+      for (; tt < nt; tt += 12) {
+        int ti2 = ti, tj2 = tj + 6;
         while (tj2 > ti2) tj2 -= ti2 + 1, ti2++;
-        const bool has2 = tt + 7 < nt;
+        const bool has2 = tt + 6 < nt;
         const double* xa = X + (8 * ti + g) * LDQ + t;
         const double* xb = X + (8 * tj + g) * LDQ + t;
         const double* ya = X + (8 * (has2 ? ti2 : ti) + g) * LDQ + t;
@@ -294,8 +319,8 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
           dv.x -= d0, dv.y -= d1;
           *dp = dv;
         }
-        // advance (ti, tj) by 14 tiles in the row-major lower-triangular enumeration
-        tj += 14;
+        // advance (ti, tj) by 12 tiles in the row-major lower-triangular enumeration
+        tj += 12;
         while (tj > ti) tj -= ti + 1, ti++;
       }
     }
@@ -391,6 +416,7 @@ __device__ __forceinline__ void invertTile(const double* S, double* Wm, double* 
     const int ti = tile >> 2, tj = tile & 3;
     tileMma(Wm + (64 + 8 * ti) * LDE + 8 * tj, LDE, Wm + (64 + 8 * ti) * LDE + 64, LDE, T + 8 * tj, LDE, 32, -1.0, g, t);
   }
+  fenceProxyAsync();  // Wm leaves by a bulk copy (async proxy)
   consumerBar();
 }
 
@@ -691,10 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       consumerBar();
       // one fence by the releasing thread after the barrier (the pattern of a grid sync): the barrier orders the CTA's
       // stores before it, the release is cumulative at gpu scope
-      if (tid == 0) {
-        __threadfence();
-        stRelease(p.done + (int64_t)bi * p.nbc + c, p.epoch);
-      }
+      if (tid == 0) stRelease(p.done + (int64_t)bi * p.nbc + c, p.epoch);  // release at gpu scope is cumulative over the barrier
       __syncthreads();  // (B)
       cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
       continue;
@@ -761,16 +784,19 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 6; j++) {
           const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
-          const double2 v = make_double2(x[i][j][0], x[i][j][1]);
-          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = v;
-          if (rowA0 + r < p.rows) *reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc) = v;
+          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(x[i][j][0], x[i][j][1]);
         }
+      LC_STAMP(13)
+      fenceProxyAsync();  // L1 goes to global by bulk copies out of E0 (below): off the chain, no store round trips here
     }
+    LC_STAMP(14)
     for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
+    LC_STAMP(15)
     consumerBar();
-    if (c >= 0 && tid == 0) {
-      __threadfence();
-      stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+    const bool l1Store = c >= 0 && tid < TB && rowA0 + tid < p.rows;
+    if (l1Store) {  // one row each (768 bytes; the block column c = d - 1 is never the partial last one)
+      bulkStore(A + ((int64_t)rowA0 + tid) * ld + (int64_t)c * TB, smemU32(E0 + tid * LDE), TB * 8);
+      bulkCommit();
     }
     LC_STAMP(5)
     // 3. D = P - L1 L1^T on the 78 lower tiles, spread over the eight warps (tile tt -> warp tt mod 8), straight into S
@@ -826,7 +852,9 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
           }
         }
     }
+    if (l1Store) bulkWaitAll();  // L(d,d-1) has landed (issued before the products: long done)
     consumerBar();
+    if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
     LC_STAMP(7)
     potrfTile(S, nd, colbuf, tid, warp, lane, (p.dbg && d == 20) ? p.dbg + 63 * 16 : nullptr);
     LC_STAMP(8)
@@ -851,13 +879,14 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     if (d + 1 < p.nbr) {  // somebody below needs W_d = L(d,d)^-1: first, it is on the critical path
       invertTile(S, E0, reinterpret_cast<double*>(smem + kSmemT), tid, warp, lane);
       LC_STAMP(9)
-      double* __restrict__ W = p.wbuf + (int64_t)d * TB * LDE;
-      for (int idx = tid; idx < TB * LDE / 2; idx += kConsumers)
-        *reinterpret_cast<double2*>(W + 2 * idx) = *reinterpret_cast<const double2*>(E0 + 2 * idx);
-      consumerBar();
+      // W_d -> global by ONE bulk copy out of E0 (invertTile ends with a proxy fence + barrier); thread 0 publishes the
+      // flag as soon as the copy has completed, the others go on with L(d,d)
       if (tid == 0) {
-        __threadfence();
+        bulkStore(p.wbuf + (int64_t)d * TB * LDE, smemU32(E0), TB * LDE * 8);
+        bulkCommit();
+        bulkWaitAll();
         stRelease(p.wdone + d, p.epoch);
+        if (p.dbg && bi < 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[bi * 16 + 12]));
       }
       LC_STAMP(10)
     }

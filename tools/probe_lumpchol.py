@@ -63,9 +63,11 @@ for uf in ufs:
     chain = rows[:, 3:9].sum(axis=1)
     print("chain (trsm .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
     # W_d flag time differences between consecutive diag jobs = the realized chain step
-    w10 = st_[1:nb, 10]
+    w10 = st_[1:nb, 12]  # %globaltimer (ns) when W_d was published: the per-SM clock64 stamps do not compare across CTAs
     w10 = w10[w10 > 0]
-    print("W flag to W flag (cycles): mean", np.diff(w10).mean(), "=", np.diff(w10).mean() / 1.965e3, "us per block column")
+    print("W flag to W flag: mean", np.diff(w10).mean() / 1e3, "us per block column (median", np.median(np.diff(w10)) / 1e3, ")")
+    sub = st_[2:nb - 1]
+    print("store_L1+zeroS split [x->E0, proxy fence, zero S, barrier+issue]:", [int((sub[:, b_] - sub[:, a_]).mean()) for a_, b_ in ((4, 13), (13, 14), (14, 15), (15, 5))])
     ps = st_[63]
     print("potrf panel stamps (d = 20), panel 0:", [int(ps[i + 1] - ps[i]) for i in range(5)], "panel 1:", [int(ps[8 + i + 1] - ps[8 + i]) for i in range(5)],
           " [solve rows, barrier, warp-0 tile update, factor 8x8, barrier]")
