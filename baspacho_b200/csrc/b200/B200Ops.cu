@@ -509,7 +509,9 @@ struct B200NumericCtx : NumericCtx<TT> {
         // the wide lumps of a level are independent of each other (and of the level's small lumps): with two or more
         // of them, each runs its whole chain (updates from its sources, blocked factorization of its column) on its
         // own lane - stream, GEMM temp, span-to-chain table, panel counters - between two joins with the main stream
-        const bool concurrent = sym.numLanes > 1 && L.bigLumps.size() >= 2 && !profileEnabled();
+        // (the per-class profiler serialises the lanes to time every launch alone, unless it is asked for the timeline)
+        static const bool timeline = getenv("BSPB200_PROFILE_TIMELINE") && atoi(getenv("BSPB200_PROFILE_TIMELINE")) != 0;
+        const bool concurrent = sym.numLanes > 1 && L.bigLumps.size() >= 2 && (!profileEnabled() || timeline);
         if (concurrent) {
           sym.ensureLanes(m.batch, laneTempBytes());
           const int used = (int)std::min<size_t>(sym.lanes.size(), L.bigLumps.size());

@@ -1,6 +1,8 @@
 // Per-kernel-class event profiler of the B200 backend (see B200Defs.h).
 #include <map>
 #include <mutex>
+#include <sstream>
+#include <cstdlib>
 #include "B200Defs.h"
 
 namespace BaSpaCho {
@@ -11,6 +13,7 @@ struct Rec {
   int cls;
   double flops, bytes;
   cudaEvent_t e0, e1;
+  cudaStream_t st;
 };
 struct State {
   bool enabled = false;
@@ -56,7 +59,7 @@ bool profileEnabled() { return state().enabled; }
 void profileBegin(cudaStream_t st, int cls, double flops, double bytes) {
   State& s = state();
   std::lock_guard<std::mutex> lock(s.mu);
-  Rec r{cls, flops, bytes, s.getEvent(), s.getEvent()};
+  Rec r{cls, flops, bytes, s.getEvent(), s.getEvent(), st};
   B200_CUDA(cudaEventRecord(r.e0, st));
   s.recs.push_back(r);
 }
@@ -73,10 +76,26 @@ std::string profileReportJson() {
   B200_CUDA(cudaDeviceSynchronize());
   double ms[KC_COUNT] = {0}, flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0};
   int64_t n[KC_COUNT] = {0};
+  // BSPB200_PROFILE_TIMELINE=1: every record as [class, stream index, start ms, end ms, flops] relative to the first
+  // record (events of different streams share the device's time base): where the lanes of a tree level overlap and
+  // where they wait
+  const char* tl = getenv("BSPB200_PROFILE_TIMELINE");
+  const bool timeline = tl && atoi(tl) != 0 && !s.recs.empty();
+  std::stringstream tss;
+  tss.precision(7);
+  std::map<cudaStream_t, int> streamIdx;
   for (Rec& r : s.recs) {
     float t = 0;
     B200_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
     ms[r.cls] += t, flops[r.cls] += r.flops, bytes[r.cls] += r.bytes, n[r.cls]++;
+    if (timeline) {
+      float t0 = 0;
+      B200_CUDA(cudaEventElapsedTime(&t0, s.recs.front().e0, r.e0));
+      const int si = streamIdx.emplace(r.st, (int)streamIdx.size()).first->second;
+      tss << (&r == &s.recs.front() ? "" : ", ") << "[" << r.cls << ", " << si << ", " << t0 << ", " << t0 + t << ", " << r.flops << "]";
+    }
+  }
+  for (Rec& r : s.recs) {
     s.pool.push_back(r.e0);
     s.pool.push_back(r.e1);
   }
@@ -84,6 +103,7 @@ std::string profileReportJson() {
   std::stringstream ss;
   ss.precision(10);
   ss << "{";
+  if (timeline) ss << "\"timeline\": [" << tss.str() << "], ";
   for (int c = 0; c < KC_COUNT; c++)
     ss << (c ? ", " : "") << "\"" << kNames[c] << "\": {\"launches\": " << n[c] << ", \"ms\": " << ms[c]
        << ", \"flops\": " << flops[c] << ", \"bytes\": " << bytes[c] << "}";

@@ -55,6 +55,9 @@ constexpr int kSmemT = kSmemY + 4 * TB * 8;           // [2][32][LDE] scratch of
 constexpr int kSmemBar = kSmemT + 2 * 32 * LDE * 8;   // mbarriers
 constexpr int kSmemBytes = kSmemBar + 128 + 1024;     // + alignment slack
 static_assert(NST * kStageBytes <= kSmemCol, "the pipeline stages alias the epilogue buffers");
+static_assert(kSmemE1 == kSmemE0 + TB * LDE * 8, "the chain CTA ping-pongs between E0 and E1");
+constexpr int kPkDoubles = 78 * 64;                    // packed lower 8 x 8 tiles of a diagonal block
+constexpr int kMbufDoubles = TB * LDE + kPkDoubles;    // accumulated operands of one diagonal block in global memory
 
 struct LcParams {
   double* A;
@@ -65,6 +68,9 @@ struct LcParams {
   int chainCtas;        // the first chainCtas CTAs to arrive work through the diagonal jobs, in order
   unsigned* done;       // [nbr * nbc] tile flags (epoch valued)
   unsigned* wdone;      // [nbc] inverse flags
+  unsigned* mdone;      // [nbc] flags of the accumulated operands of the diagonal blocks (mbuf): M1 ..
+  unsigned* pdone;      // .. and P
+  double* mbuf;         // [nbc][kMbufDoubles]: M1 = A(d,d-1) - sum ([96][LDE]) and P = A(d,d) - sum (78 packed 8 x 8 tiles)
   unsigned* ctr;        // [0] ticket of the regular jobs, [2] arrival counter, [3] ticket of the diagonal jobs (never reset)
   unsigned ticketBase, arriveBase, diagBase;
   unsigned* abortFlag;  // holds the epoch of the launch that timed out (never reset)
@@ -165,11 +171,11 @@ __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, u
 // shuffle -> rsqrt -> scale -> shuffle -> FMA (~200 cycles); the same factorization with every lane holding the whole tile
 // in registers measured 2.2 k cycles per tile (the 110 independent updates of a tile compete with the chain for the
 // issue slots of the one warp).
-// The tile is factored in place in D (row stride LDQ, lower triangle) and the reciprocal pivots go to rsOut[8] for the
-// panel solves. Round 2c: the 32 lanes all run the whole 8 x 8 factorization redundantly on their own copy (the
+// The tile is factored in place in D (row stride LDQ, lower triangle) and the inverse of the factor (row-major 8 x 8) goes to
+// invOut[64] for the panel solves. Round 2c: the 32 lanes all run the whole 8 x 8 factorization redundantly on their own copy (the
 // lane-distributed version spent 2.2 k cycles per tile in the shuffles of its 8 pivot steps; the warp has nothing
 // else to do there). e < 8: columns >= e act as identity; rows >= e of the tile ride along (they come out as M L^-T).
-__device__ __forceinline__ void factorTile8(double* D, int e, double* rsOut, int lane) {
+__device__ __forceinline__ void factorTile8(double* D, int e, double* invOut, int lane) {
   // every lane holds the whole lower triangle (broadcast loads, static register indices): no shuffle on the pivot chain
   double a[8][8];
 #pragma unroll
@@ -196,6 +202,26 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* rsOut, int
       for (int r = c; r < 8; r++) a[r][c] = (r == c) ? 1.0 : 0.0;
     }
   }
+  // inverse of the factor for the panel solves (X = M L^-T on the tensor pipe): lane j < 8 builds column j by forward
+  // substitution (the other lanes repeat the work of lane j & 7). Rows >= e count as identity rows here.
+  {
+    const int j = lane & 7;
+    double w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      double v = (i == j) ? 1.0 : 0.0;
+      if (i < e) {
+#pragma unroll
+        for (int q = 0; q < i; q++) v -= a[i][q] * w[q];
+        v *= rs[i];
+      }
+      w[i] = v;
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) invOut[i * 8 + j] = w[i];
+    }
+  }
   // lane 0 writes the tile back (one predicate for straight-line vector stores: a store per lane-and-entry predicate
   // compiled into a divergent jump table, 10 k cycles). The entry right of the diagonal of an even row rides along.
   if (lane == 0) {
@@ -203,8 +229,6 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* rsOut, int
     for (int r = 0; r < 8; r++)
 #pragma unroll
       for (int c = 0; c <= (r | 1); c += 2) *reinterpret_cast<double2*>(D + r * LDQ + c) = make_double2(a[r][c], a[r][c + 1]);
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(rsOut + c) = make_double2(rs[c], rs[c + 1]);
   }
 }
 
@@ -221,7 +245,7 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* rsOut, int
 __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane,
                                           long long* dbgp = nullptr /* diagnostics: 16 stamps of the first two panels */) {
   const int g = lane >> 2, t = lane & 3;
-  if (warp == 0) factorTile8(S, min(8, nd), fac2 + 64, lane);
+  if (warp == 0) factorTile8(S, min(8, nd), fac2, lane);
   __syncthreads();
 #pragma unroll 1
   for (int j0 = 0, pb = 0; j0 < nd; j0 += 8, pb ^= 1) {
@@ -232,36 +256,18 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
 #define LC_PSTAMP(i) \
   if (dbgp && tid == 0 && j0 < 16) dbgp[(j0 >> 3) * 8 + (i)] = clock64();
     LC_PSTAMP(0)
-    // (b) rows below the diagonal tile: right-looking substitution (two dependent operations per column)
-    const int r = j0 + 8 + tid;
-    if (r < TB) {
-      const double* Dt = S + j0 * LDQ + j0;  // the factored diagonal tile (broadcast reads)
-      double* xr = S + r * LDQ + j0;
-      double x[8];
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(xr + c);
-        x[c] = v.x, x[c + 1] = v.y;
+    // (b) rows below the diagonal tile: X = M L^-T, one 8 x 8 tile (two DMMA) at a time, tiles over the warps. (A thread
+    // per row by substitution measured ~800 cycles per panel: 36 dependent fp64 operations.)
+    {
+      const double b0 = fac[g * 8 + t], b1 = fac[g * 8 + 4 + t];  // "col" fragment of L^-T: B[k][n] = Linv[n][k]
+      for (int tile = warp; tile < m; tile += 8) {
+        double* xt = S + (j0 + 8 + 8 * tile + g) * LDQ + j0;
+        double c0 = 0.0, c1 = 0.0;
+        dmma(c0, c1, xt[t], b0);
+        dmma(c0, c1, xt[4 + t], b1);
+        __syncwarp();  // every lane has read its fragments of the tile
+        *reinterpret_cast<double2*>(xt + 2 * t) = make_double2(c0, c1);
       }
-      double Lt[8][8];
-#pragma unroll
-      for (int j = 1; j < 8; j++)
-#pragma unroll
-        for (int c = 0; c < j; c += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(Dt + j * LDQ + c);
-          Lt[j][c] = v.x, Lt[j][c + 1] = v.y;
-        }
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (c < e) {
-          x[c] *= fac[64 + c];
-#pragma unroll
-          for (int j = c + 1; j < 8; j++)
-            if (j < e) x[j] -= x[c] * Lt[j][c];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(xr + c) = make_double2(x[c], x[c + 1]);
     }
     LC_PSTAMP(1)
     __syncthreads();
@@ -282,7 +288,7 @@ __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2]
       *cp = cv;
       if (j0 + 8 < nd) {
         __syncwarp();
-        factorTile8(C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72 + 64, lane);
+        factorTile8(C, min(8, nd - j0 - 8), fac2 + (pb ^ 1) * 72, lane);
       }
       LC_PSTAMP(4)
     } else if (warp != 4) {
@@ -568,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   double* ybuf = reinterpret_cast<double*>(smem + kSmemY);
   const uint32_t stagesBase = smemU32(smem);
   const uint32_t fullBar0 = smemU32(smem + kSmemBar), emptyBar0 = fullBar0 + 8 * NST, wBar = fullBar0 + 16 * NST;
+  const uint32_t mBar = wBar + 8, pBar = wBar + 16;  // chain CTA: M1 / P of the next diagonal block have landed
   __shared__ int jobS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = tid == 0;
@@ -584,12 +591,14 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       mbarInit(emptyBar0 + 8 * s, kConsumers / 32);
     }
     mbarInit(wBar, 1);
+    mbarInit(mBar, 1);
+    mbarInit(pBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
 #define LC_STAMP(i) \
-  if (p.dbg && tid == 0 && job.diag && bi < 64) p.dbg[bi * 16 + (i)] = clock64();
+  if (p.dbg && tid == 0 && job.diag == 1 && bi < 64) p.dbg[bi * 16 + (i)] = clock64();
   long long cycMain = 0, cycEpi = 0, cycWait = 0, nJobs = 0;
   unsigned wUses = 0;  // bulk loads of a block inverse so far (phase of wBar)
   unsigned it = 0;  // pipeline iteration counter, continues across the jobs of this CTA (producer and consumers agree)
@@ -597,9 +606,199 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   const int64_t ld = p.ld;
 
   __shared__ int chainS;
-  if (tid == 0) chainS = (int)(atomicAdd(p.ctr + 2, 1u) - p.arriveBase) < p.chainCtas;
+  if (tid == 0) chainS = (int)(atomicAdd(p.ctr + 2, 1u) - p.arriveBase);
   __syncthreads();
-  bool chain = chainS != 0;
+  const int arrival = chainS;
+  // arrival 0: THE chain CTA (serial part of every diagonal block); arrivals 1 .. chainCtas: accumulate the operands of
+  // the diagonal blocks ahead of it; everybody else (and those, once they run out of their own work): regular tiles
+  bool chain = arrival >= 1 && arrival <= p.chainCtas;
+  if (arrival == 0) {
+    // ================================================================================ the chain of diagonal blocks
+    // Step d:  L1 = L(d,d-1) = M1 W_{d-1}^T  ->  D = P - L1 L1^T  ->  potrf(D)  ->  W_d = L(d,d)^-1, with W_{d-1} still in
+    // shared memory from the previous step (no flag hop, no store / load of the inverse on the chain) and M1, P arriving
+    // from the accumulate jobs by bulk copies. The two 96 x LDE buffers swap roles every step: W_{d-1} | M1 -> X = L1,
+    // then D is built over the dead W_{d-1} and W_d over the dead L1.
+    double* Tk = reinterpret_cast<double*>(smem + kSmemT);  // P (packed tiles) until D is built, then inversion scratch
+    unsigned mUses = 0, pUses = 0;
+    bool wPending = false;  // thread 0: W_{d-1} is on its way to global memory, flag not yet published
+    // thread 0: the operands of block dd, M1 into dstM; `block` = false: only if they are already published
+    auto requestOperands = [&](int dd, double* dstM, bool block) -> bool {
+      if (*(volatile unsigned*)p.abortFlag != p.epoch) {
+        if (!block && ((dd > 0 && ldAcquire(p.mdone + dd) != p.epoch) || ldAcquire(p.pdone + dd) != p.epoch)) return false;
+        const long long t0 = clock64();
+        if (dd > 0) waitFlag(p.mdone + dd, p.epoch, p.abortFlag);
+        waitFlag(p.pdone + dd, p.epoch, p.abortFlag);
+        cycWait += clock64() - t0;
+      }
+      fenceProxyAsync();
+      const double* src = p.mbuf + (int64_t)dd * kMbufDoubles;
+      if (dd > 0) {
+        mbarArriveExpectTx(mBar, TB * LDE * 8);
+        bulkLoad(smemU32(dstM), src, TB * LDE * 8, mBar);
+      }
+      mbarArriveExpectTx(pBar, kPkDoubles * 8);
+      bulkLoad(smemU32(Tk), src + TB * LDE, kPkDoubles * 8, pBar);
+      return true;
+    };
+#define LC_CSTAMP(i) \
+  if (p.dbg && tid == 0 && d < 64) p.dbg[d * 16 + (i)] = clock64();
+    if (tid == 0) requestOperands(0, E1, true);
+    const long long tChain = clock64();
+    for (int d = 0; d < p.nbc; d++) {
+      const int par = d & 1;
+      double* Ea = E0 + par * (TB * LDE);        // W_{d-1}, then the diagonal block
+      double* Eb = E0 + (par ^ 1) * (TB * LDE);  // M1, then L1, then W_d
+      double* S = Ea;
+      const int c = d - 1, rowA0 = d * TB;
+      const int nd = min(TB, p.n - d * TB);
+      const int rbase = 24 * wm;
+      LC_CSTAMP(0)
+      if (p.dbg && tid == 0 && d < 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[d * 16 + 2]));
+      if (c >= 0) {
+        mbarWait(mBar, mUses & 1);
+        mUses++;
+        LC_CSTAMP(3)
+        double x[3][6][2];
+        trsmProduct(x, Eb, Ea, rbase, wn, g, t);
+        if (tid == 0 && wPending) {  // W_{d-1}: the copy out of Ea has had the whole product to complete
+          bulkWaitAll();
+          stRelease(p.wdone + c, p.epoch);
+          if (p.dbg && c < 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[c * 16 + 12]));
+          wPending = false;
+        }
+        consumerBar();  // every read of M1 and W_{d-1} is done
+        LC_CSTAMP(4)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
+            *reinterpret_cast<double2*>(Eb + r * LDE + cc) = make_double2(x[i][j][0], x[i][j][1]);
+          }
+        fenceProxyAsync();  // L1 goes to global by bulk copies out of Eb
+      }
+      // a full interior block overwrites its whole lower triangle below (what is left of W_{d-1} above the diagonal of
+      // the diagonal tiles is never read); a partial one must be zero outside its valid region
+      if (nd < TB || rowA0 + TB > p.rows)
+        for (int idx = tid; idx < TB * LDQ / 2; idx += kConsumers) reinterpret_cast<double2*>(S)[idx] = make_double2(0.0, 0.0);
+      consumerBar();
+      const bool l1Store = c >= 0 && tid < TB && rowA0 + tid < p.rows;
+      if (l1Store) {  // one row each (768 bytes; the block column c = d - 1 is never the partial last one)
+        bulkStore(A + ((int64_t)rowA0 + tid) * ld + (int64_t)c * TB, smemU32(Eb + tid * LDE), TB * 8);
+        bulkCommit();
+      }
+      LC_CSTAMP(5)
+      mbarWait(pBar, pUses & 1);  // P has landed
+      pUses++;
+      // D = P - L1 L1^T on the 78 lower tiles, straight into S. Warp (wm, wn): three tile rows chosen so that every wm
+      // holds 18 - 21 lower tiles ({11,4,1}, {10,5,2}, {9,6,3}, {8,7,0}), column tiles 2 j + wn: 9 fragment loads per 18
+      // DMMA, and the two warps of an SM sub-partition (same wm) carry the same load
+      {
+        double y[3][6][2];
+        int rowT[3];
+        rowT[0] = 11 - wm, rowT[1] = wm == 3 ? 7 : 4 + wm, rowT[2] = wm == 3 ? 0 : 1 + wm;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) y[i][j][0] = y[i][j][1] = 0.0;
+        if (c >= 0) {
+          const double* bs = Eb + (8 * wn + g) * LDE + t;
+          // live column tiles of row i: 2 j + wn <= rowT[i]; dead ones skipped by a real branch (see trsmProduct)
+          int nact[3];
+#pragma unroll
+          for (int i = 0; i < 3; i++) nact[i] = rowT[i] >= wn ? (rowT[i] - wn) / 2 + 1 : 0;
+#pragma unroll 1
+          for (int kk = 0; kk < TB; kk += 4) {
+            double bf[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              const double a = Eb[(8 * rowT[i] + g) * LDE + kk + t];
+              switch (nact[i]) {
+                case 6: dmma(y[i][5][0], y[i][5][1], a, bf[5]);
+                case 5: dmma(y[i][4][0], y[i][4][1], a, bf[4]);
+                case 4: dmma(y[i][3][0], y[i][3][1], a, bf[3]);
+                case 3: dmma(y[i][2][0], y[i][2][1], a, bf[2]);
+                case 2: dmma(y[i][1][0], y[i][1][1], a, bf[1]);
+                case 1: dmma(y[i][0][0], y[i][0][1], a, bf[0]);
+                default: break;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const int ti = rowT[i], tj = 2 * j + wn;
+            if (tj <= ti) {
+              const double2 pv = *reinterpret_cast<const double2*>(Tk + (ti * (ti + 1) / 2 + tj) * 64 + g * 8 + 2 * t);
+              const int r = 8 * ti + g, cc = 8 * tj + 2 * t;
+              // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride
+              // along the factorization as the extra rows of a trapezoid: they come out as M L^-T
+              if (cc <= r && cc < nd && rowA0 + r < p.rows) S[r * LDQ + cc] = pv.x - y[i][j][0];
+              if (cc + 1 <= r && cc + 1 < nd && rowA0 + r < p.rows) S[r * LDQ + cc + 1] = pv.y - y[i][j][1];
+            }
+          }
+      }
+      if (l1Store) bulkWaitAll();  // L(d,d-1) has landed (issued before the products: long done)
+      consumerBar();
+      if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+      LC_CSTAMP(7)
+      potrfTile(S, nd, colbuf, tid, warp, lane, (p.dbg && d == 20) ? p.dbg + 63 * 16 : nullptr);
+      LC_CSTAMP(8)
+      // L(d,d) -> global (lower triangle, coalesced rows): plain stores, nobody inside the launch waits for them
+      for (int r = warp; r < nd; r += 8)
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          const int cc = lane + 32 * u;
+          if (cc <= r) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
+        }
+      if (nd < TB) {
+        // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion
+        for (int r = nd + warp; r < TB; r += 8)
+          if (rowA0 + r < p.rows) {
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              const int cc = lane + 32 * u;
+              if (cc < nd) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
+            }
+          }
+        consumerBar();
+        for (int idx = tid; idx < (TB - nd) * TB; idx += kConsumers) {
+          const int r = nd + idx / TB, cc = idx % TB;
+          S[r * LDQ + cc] = (r == cc) ? 1.0 : 0.0;
+        }
+        for (int idx = tid; idx < nd * (TB - nd); idx += kConsumers) S[(idx / (TB - nd)) * LDQ + nd + idx % (TB - nd)] = 0.0;
+        consumerBar();
+      }
+      if (d + 1 < p.nbr) {  // somebody below needs W_d = L(d,d)^-1
+        invertTile(S, Eb, Tk, tid, warp, lane);  // ends with a proxy fence + barrier: S and the scratch are dead after it
+        LC_CSTAMP(9)
+        if (tid == 0) {
+          bulkStore(p.wbuf + (int64_t)d * TB * LDE, smemU32(Eb), TB * LDE * 8);
+          bulkCommit();
+          // the next block's operands: M1 over the dead diagonal block. When they are already there (the usual case) the
+          // chain goes straight on and W_d is published from inside the next step, once its copy has completed (~5 k
+          // cycles that thread 0 - and with it the next triangular product - would otherwise wait here); else W_d is
+          // published first (regular tiles wait for it) and the request blocks
+          wPending = d + 1 < p.nbc && requestOperands(d + 1, Ea, false);
+          if (!wPending) {
+            bulkWaitAll();
+            stRelease(p.wdone + d, p.epoch);
+            if (p.dbg && d < 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[d * 16 + 12]));
+            if (d + 1 < p.nbc) requestOperands(d + 1, Ea, true);
+          }
+        }
+        LC_CSTAMP(10)
+      }
+    }
+#undef LC_CSTAMP
+    fenceProxyAsync();
+    __syncthreads();
+    cycEpi += clock64() - tChain, nJobs += p.nbc;
+  }
 
   for (;;) {
     Job job;
@@ -608,11 +807,13 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       __syncthreads();
       const int dj = jobS;
       __syncthreads();
-      if (dj >= p.nbc) {  // the chain is finished (or about to be): help with the regular tiles
+      if (dj >= 2 * p.nbc - 1) {  // every accumulate job is taken: help with the regular tiles
         chain = false;
         continue;
       }
-      job.i = dj, job.c = dj - 1, job.diag = 1;
+      // ticket 0: P of block 0; then, for d = 1, 2, ..: M1 of block d (diag = 1), P of block d (diag = 2)
+      const int dd = (dj + 1) >> 1;
+      job.i = dd, job.c = dd - 1, job.diag = dj == 0 ? 2 : 1 + ((dj + 1) & 1);
     } else {
       if (tid == 0) jobS = (int)(atomicAdd(p.ctr, 1u) - p.ticketBase);
       __syncthreads();
@@ -622,17 +823,19 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     }
     const int c = job.c, bi = job.i;
     const int kTiles = c > 0 ? c * (TB / BK) : 0;  // K = 96 c
-    const int rowA0 = bi * TB, rowB0 = (c < 0 ? 0 : c) * TB;
+    // block row of the B operand: c for a tile (i, c) - regular tiles and M1 = (d, d-1) -, d itself for P = (d, d)
+    const int browB = job.diag == 2 ? bi : (c < 0 ? 0 : c);
+    const int rowA0 = bi * TB, rowB0 = browB * TB;
 
     const long long tJob = clock64();
-    LC_STAMP(0)
+    LC_STAMP(13)
     if (c >= 0 || job.diag) {
       // the tiles' own (original) entries are only needed after the K loop: pull them into L2 now, one 128-byte line
       // per request, so that the epilogue does not wait for HBM (diagonal jobs measured ~10 us there, on the chain)
-      const int cols0 = (c >= 0 ? c : 0) * TB, nlines = job.diag ? 2 * TB * 6 : TB * 6;
-      for (int idx = tid; idx < nlines; idx += kConsumers) {
-        const int r = (idx / 6) % TB, l = idx % 6, second = idx / (TB * 6);
-        const int64_t gr = (int64_t)rowA0 + r, gc = (int64_t)(second ? bi * TB : cols0) + l * 16;
+      const int cols0 = (job.diag == 2 ? bi : (c >= 0 ? c : 0)) * TB;
+      for (int idx = tid; idx < TB * 6; idx += kConsumers) {
+        const int r = idx / 6, l = idx % 6;
+        const int64_t gr = (int64_t)rowA0 + r, gc = (int64_t)cols0 + l * 16;
         if (gr < p.rows && gc < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + gr * ld + gc));
       }
     }
@@ -642,18 +845,15 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 12; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     LoadCtx lc;
-    lc.tmap = &tmap, lc.doneA = p.done + (int64_t)bi * p.nbc, lc.doneB = p.done + (int64_t)(c < 0 ? 0 : c) * p.nbc;
-    lc.abortFlag = p.abortFlag, lc.epoch = p.epoch, lc.rowA0 = rowA0, lc.rowB0 = rowB0, lc.nBTiles = job.diag ? 2 : 1;
+    lc.tmap = &tmap, lc.doneA = p.done + (int64_t)bi * p.nbc, lc.doneB = p.done + (int64_t)browB * p.nbc;
+    lc.abortFlag = p.abortFlag, lc.epoch = p.epoch, lc.rowA0 = rowA0, lc.rowB0 = rowB0, lc.nBTiles = 1;
     lc.ok = *(volatile unsigned*)p.abortFlag != p.epoch;
     lc.waitCycles = 0;
-    if (job.diag)
-      mainLoop<12>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 96 * wn, g, t, lane, producer, lc);
-    else
-      mainLoop<6>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane, producer, lc);
+    mainLoop<6>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane, producer, lc);
     __syncthreads();  // (A) every stage has been consumed: the stage memory becomes the epilogue workspace
     const long long tMain = clock64();
     cycWait += lc.waitCycles;
-    LC_STAMP(1)
+    LC_STAMP(14)
 
     const int nc = c >= 0 ? min(TB, p.n - c * TB) : 0;  // valid columns of block column c
     // W_c -> E1 by one bulk copy (the buffer holds the padded operand layout). Requested right away when W_c is already
@@ -673,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       bulkLoad(smemU32(E1), p.wbuf + (int64_t)c * TB * LDE, TB * LDE * 8, wBar);
       wIssued = true;
     };
-    if (tid == 0) requestW(false);
+    if (tid == 0 && !job.diag) requestW(false);
     if (!job.diag) {
       // ---- regular tile: M = A(i,c) - acc -> E0 ; W_c -> E1 ; X = M W^T -> global
       const int rbase = 24 * wm, cbase = 48 * wn;
@@ -723,183 +923,59 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
       continue;
     }
 
-    // ---- diagonal job of block d = bi: tiles T1 = (d, d-1) (accumulated by the warps wn = 0) and T2 = (d, d) (wn = 1)
+    // ---- accumulate job of block d = bi: M1 = A(d,d-1) - sum (diag = 1) or P = A(d,d) - sum (diag = 2, lower tiles,
+    // packed) goes to the block's slot of mbuf; the chain CTA picks them up with two bulk copies when it gets there
     const int d = bi;
     const int nd = min(TB, p.n - d * TB);  // valid rows / columns of the diagonal block
-    const int rbase = 24 * wm;
-    double* S = E1;                                               // [96][LDQ] diagonal block, once W is dead
-    double* Pk = reinterpret_cast<double*>(smem + kSmemT);        // packed lower 8 x 8 tiles of A(d,d) - acc2 (40 KB)
-    // 1. everything that does not need W_{d-1}: M1 = A(d,d-1) - acc1 -> E0 (operand of the triangular product) and
-    //    P = A(d,d) - acc2 -> packed tiles (the original entries are fetched here, off the critical chain)
-    if (wn == 0) {
-      if (c >= 0) {
+    const int rbase = 24 * wm, cbase = 48 * wn;
+    double* __restrict__ mb = p.mbuf + (int64_t)d * kMbufDoubles;
+    if (job.diag == 1) {
+      double2 av[3][6];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {  // twelve loads in flight per round trip
-          double2 av[12];
-          const int r = rbase + 8 * i + g;
+      for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 12; j++) {
-            av[j] = make_double2(0.0, 0.0);
-            if (rowA0 + r < p.rows)
-              av[j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + 8 * j + 2 * t));
-          }
-#pragma unroll
-          for (int j = 0; j < 12; j++)
-            *reinterpret_cast<double2*>(E0 + r * LDE + 8 * j + 2 * t) =
-                make_double2(av[j].x - acc[i][j][0], av[j].y - acc[i][j][1]);
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          av[i][j] = make_double2(0.0, 0.0);
+          if (rowA0 + r < p.rows) av[i][j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + c * TB + cc));
         }
-      }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          __stcg(reinterpret_cast<double2*>(mb + r * LDE + cc), make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]));
+        }
     } else {
+      double* __restrict__ pk = mb + TB * LDE;
+      double2 av[3][6];
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const int ti = 3 * wm + i, r = rbase + 8 * i + g;
-        double2 av[12];
+      for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 12; j++) {  // lower tiles only (warp uniform)
-          av[j] = make_double2(0.0, 0.0);
-          if (j <= ti && 8 * j + 2 * t < nd && rowA0 + r < p.rows)
-            av[j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)d * TB + 8 * j + 2 * t));
+        for (int j = 0; j < 6; j++) {  // lower tiles only (warp uniform)
+          const int ti = 3 * wm + i, tj = 6 * wn + j, r = rbase + 8 * i + g, cc = 8 * tj + 2 * t;
+          av[i][j] = make_double2(0.0, 0.0);
+          if (tj <= ti && cc < nd && rowA0 + r < p.rows)
+            av[i][j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc));
         }
-#pragma unroll
-        for (int j = 0; j < 12; j++)
-          if (j <= ti)
-            *reinterpret_cast<double2*>(Pk + (ti * (ti + 1) / 2 + j) * 64 + g * 8 + 2 * t) =
-                make_double2(av[j].x - acc[i][j][0], av[j].y - acc[i][j][1]);
-      }
-    }
-    LC_STAMP(2)
-    if (tid == 0) requestW(true);
-    consumerBar();
-    if (c >= 0) {
-      // 2. L1 = L(d,d-1) = M1 W^T by all eight warps (24 x 48 each)
-      mbarWait(wBar, wUses & 1);
-      wUses++;
-      LC_STAMP(3)
-      double x[3][6][2];
-      trsmProduct(x, E0, E1, rbase, wn, g, t);
-      consumerBar();  // every read of M1 and W is done: E0 becomes L1, E1 becomes the diagonal block
-      LC_STAMP(4)
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-          const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
-          *reinterpret_cast<double2*>(E0 + r * LDE + cc) = make_double2(x[i][j][0], x[i][j][1]);
+          const int ti = 3 * wm + i, tj = 6 * wn + j;
+          if (tj <= ti)
+            __stcg(reinterpret_cast<double2*>(pk + (ti * (ti + 1) / 2 + tj) * 64 + g * 8 + 2 * t),
+                   make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]));
         }
-      LC_STAMP(13)
-      fenceProxyAsync();  // L1 goes to global by bulk copies out of E0 (below): off the chain, no store round trips here
     }
-    LC_STAMP(14)
-    for (int idx = tid; idx < TB * LDQ; idx += kConsumers) S[idx] = 0.0;
     LC_STAMP(15)
-    consumerBar();
-    const bool l1Store = c >= 0 && tid < TB && rowA0 + tid < p.rows;
-    if (l1Store) {  // one row each (768 bytes; the block column c = d - 1 is never the partial last one)
-      bulkStore(A + ((int64_t)rowA0 + tid) * ld + (int64_t)c * TB, smemU32(E0 + tid * LDE), TB * 8);
-      bulkCommit();
+    __syncthreads();
+    if (tid == 0) {
+      stRelease((job.diag == 1 ? p.mdone : p.pdone) + d, p.epoch);
+      if (p.dbg && d < 64 && job.diag == 1) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[d * 16 + 1]));
+      if (p.dbg && d < 64 && job.diag == 2) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[d * 16 + 6]));
     }
-    LC_STAMP(5)
-    // 3. D = P - L1 L1^T on the 78 lower tiles, spread over the eight warps (tile tt -> warp tt mod 8), straight into S
-    {
-      // warp (wm, wn): three tile rows chosen so that every wm holds 18 - 21 lower tiles ({11,4,1}, {10,5,2}, {9,6,3},
-      // {8,7,0}), column tiles 2 j + wn: 9 fragment loads per 18 DMMA, and the two warps of an SM sub-partition
-      // (same wm) carry the same load
-      double y[3][6][2];
-      int rowT[3];
-      rowT[0] = 11 - wm, rowT[1] = wm == 3 ? 7 : 4 + wm, rowT[2] = wm == 3 ? 0 : 1 + wm;
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 6; j++) y[i][j][0] = y[i][j][1] = 0.0;
-      if (c >= 0) {
-        const double* bs = E0 + (8 * wn + g) * LDE + t;
-        // live column tiles of row i: 2 j + wn <= rowT[i]; dead ones skipped by a real branch (see trsmProduct)
-        int nact[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) nact[i] = rowT[i] >= wn ? (rowT[i] - wn) / 2 + 1 : 0;
-#pragma unroll 1
-        for (int kk = 0; kk < TB; kk += 4) {
-          double bf[6];
-#pragma unroll
-          for (int j = 0; j < 6; j++) bf[j] = bs[j * 16 * LDE + kk];
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const double a = E0[(8 * rowT[i] + g) * LDE + kk + t];
-            switch (nact[i]) {
-              case 6: dmma(y[i][5][0], y[i][5][1], a, bf[5]);
-              case 5: dmma(y[i][4][0], y[i][4][1], a, bf[4]);
-              case 4: dmma(y[i][3][0], y[i][3][1], a, bf[3]);
-              case 3: dmma(y[i][2][0], y[i][2][1], a, bf[2]);
-              case 2: dmma(y[i][1][0], y[i][1][1], a, bf[1]);
-              case 1: dmma(y[i][0][0], y[i][0][1], a, bf[0]);
-              default: break;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          const int ti = rowT[i], tj = 2 * j + wn;
-          if (tj <= ti) {
-            const double2 pv = *reinterpret_cast<const double2*>(Pk + (ti * (ti + 1) / 2 + tj) * 64 + g * 8 + 2 * t);
-            const int r = 8 * ti + g, cc = 8 * tj + 2 * t;
-            // rows >= nd of the block (rows below a partial last diagonal block, when the lump has rows below) ride along
-            // the factorization as the extra rows of a trapezoid: they come out as M L^-T
-            if (cc <= r && cc < nd && rowA0 + r < p.rows) S[r * LDQ + cc] = pv.x - y[i][j][0];
-            if (cc + 1 <= r && cc + 1 < nd && rowA0 + r < p.rows) S[r * LDQ + cc + 1] = pv.y - y[i][j][1];
-          }
-        }
-    }
-    if (l1Store) bulkWaitAll();  // L(d,d-1) has landed (issued before the products: long done)
-    consumerBar();
-    if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
-    LC_STAMP(7)
-    potrfTile(S, nd, colbuf, tid, warp, lane, (p.dbg && d == 20) ? p.dbg + 63 * 16 : nullptr);
-    LC_STAMP(8)
-    if (nd < TB) {
-      // ride-along rows -> global; then rows / columns beyond the block become identity for the inversion
-      for (int r = nd + warp; r < TB; r += 8)
-        if (rowA0 + r < p.rows) {
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            const int cc = lane + 32 * u;
-            if (cc < nd) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
-          }
-        }
-      consumerBar();
-      for (int idx = tid; idx < (TB - nd) * TB; idx += kConsumers) {
-        const int r = nd + idx / TB, cc = idx % TB;
-        S[r * LDQ + cc] = (r == cc) ? 1.0 : 0.0;
-      }
-      for (int idx = tid; idx < nd * (TB - nd); idx += kConsumers) S[(idx / (TB - nd)) * LDQ + nd + idx % (TB - nd)] = 0.0;
-      consumerBar();
-    }
-    if (d + 1 < p.nbr) {  // somebody below needs W_d = L(d,d)^-1: first, it is on the critical path
-      invertTile(S, E0, reinterpret_cast<double*>(smem + kSmemT), tid, warp, lane);
-      LC_STAMP(9)
-      // W_d -> global by ONE bulk copy out of E0 (invertTile ends with a proxy fence + barrier); thread 0 publishes the
-      // flag as soon as the copy has completed, the others go on with L(d,d)
-      if (tid == 0) {
-        bulkStore(p.wbuf + (int64_t)d * TB * LDE, smemU32(E0), TB * LDE * 8);
-        bulkCommit();
-        bulkWaitAll();
-        stRelease(p.wdone + d, p.epoch);
-        if (p.dbg && bi < 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.dbg[bi * 16 + 12]));
-      }
-      LC_STAMP(10)
-    }
-    // L(d,d) -> global (lower triangle, coalesced rows)
-    for (int r = warp; r < nd; r += 8)
-#pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const int cc = lane + 32 * u;
-        if (cc <= r) A[((int64_t)rowA0 + r) * ld + (int64_t)d * TB + cc] = S[r * LDQ + cc];
-      }
-    fenceProxyAsync();
     __syncthreads();  // (B)
-    LC_STAMP(11)
     cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
   }
 #undef LC_STAMP
@@ -935,7 +1011,7 @@ EncodeTiledFn encodeTiled() {
 struct LcState {
   DevBuf<long long> dbg;
   DevBuf<unsigned> words;
-  DevBuf<double> wbuf;
+  DevBuf<double> wbuf, mbuf;
   int nbcCap = 0;
   int64_t tileCap = 0;
   unsigned epoch = 0, ticketBase = 0, arriveBase = 0, diagBase = 0;
@@ -985,7 +1061,7 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   int64_t regular = 0;
   for (int c = 0; c < p.nbc; c++) regular += std::max(0, p.nbr - (c + 1 < p.nbc ? c + 2 : c + 1));
   p.numRegular = (int)regular;
-  const int64_t jobs = regular + p.nbc;
+  const int64_t jobs = regular + 2 * p.nbc - 1;
 
   LcState& s = lcState(st);
   const int64_t tiles = (int64_t)p.nbr * p.nbc;
@@ -993,14 +1069,16 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
     B200_CUDA(cudaStreamSynchronize(st));
     s.nbcCap = std::max(p.nbc, s.nbcCap * 2);
     s.tileCap = std::max(tiles, s.tileCap * 2);
-    s.words.resize((size_t)(4 + s.nbcCap + s.tileCap));
+    s.words.resize((size_t)(4 + 3 * s.nbcCap + s.tileCap));
     s.wbuf.resize((size_t)s.nbcCap * TB * LDE);
+    s.mbuf.resize((size_t)s.nbcCap * kMbufDoubles);
     B200_CUDA(cudaMemsetAsync(s.words.ptr(), 0, s.words.size() * sizeof(unsigned), st));
     s.epoch = 0, s.ticketBase = s.arriveBase = s.diagBase = 0;
   }
   p.ctr = s.words.ptr(), p.abortFlag = s.words.ptr() + 1, p.wdone = s.words.ptr() + 4;
-  p.done = s.words.ptr() + 4 + s.nbcCap;
-  p.wbuf = s.wbuf.ptr();
+  p.mdone = s.words.ptr() + 4 + s.nbcCap, p.pdone = s.words.ptr() + 4 + 2 * s.nbcCap;
+  p.done = s.words.ptr() + 4 + 3 * s.nbcCap;
+  p.wbuf = s.wbuf.ptr(), p.mbuf = s.mbuf.ptr();
   p.epoch = ++s.epoch, p.ticketBase = s.ticketBase, p.arriveBase = s.arriveBase, p.diagBase = s.diagBase;
   p.dbg = nullptr;
   if (const char* e = getenv("BSPB200_LUMPCHOL_DBG")) {
@@ -1024,16 +1102,20 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   int dev = 0, sms = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // CTAs: the chain of diagonal blocks bounds the run time from below (~40 us per block column); more CTAs than it
-  // takes to finish the flops in that time only spin on flags - and occupy SMs that lumps factored concurrently on
-  // other streams (independent lumps of a tree level) could use. 1.5 x the break-even count, at ~200 GF/s per SM.
+  // CTAs: the chain of diagonal blocks bounds the run time from below (~36.5 us per block column, measured); more CTAs
+  // than it takes to finish the flops in that time only spin on flags - and occupy SMs that lumps factored concurrently
+  // on other streams (independent lumps of a tree level) could use. Twice the break-even count at ~150 GF/s per SM
+  // (232 GF/s is the DMMA peak of one SM; a CTA spends ~20 % of its time waiting for source tiles), plus the chain CTA
+  // and the accumulate jobs running ahead of it. Measured (profiles/README.md): n = 2000: 24 CTAs 1.00 ms, 32: 0.80,
+  // 48: 0.77, 96: 0.77; n = 1000 + 700 rows: 16 CTAs 0.60 ms, 24: 0.44, 32: 0.41, 48: 0.41.
   const double flops = (double)n * n * n / 3 + (double)rowsBelow * n * n;
-  int64_t want = (int64_t)(1.5 * flops / (p.nbc * 40e-6 * 200e9)) + 1;
+  int64_t want = (int64_t)(2.0 * flops / (p.nbc * 36.5e-6 * 150e9)) + (int64_t)(0.4 * p.nbc) + 3;
   if (const char* e = getenv("BSPB200_LUMPCHOL_GRID")) want = atoi(e);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)sms, jobs, std::max<int64_t>(want, 16)}));
+  // at least two CTAs: the chain CTA only consumes what the accumulate jobs of the others publish
+  const int grid = (int)std::max<int64_t>(2, std::min<int64_t>({(int64_t)sms, jobs + 1, std::max<int64_t>(want, 16)}));
   // chain CTAs: a diagonal job needs ~0.4 chain steps of accumulation per block column it has behind it
   int chain = std::max(1, std::min((int)(0.4 * p.nbc) + 1, std::max(1, grid / 3)));
-  if (const char* e = getenv("BSPB200_LUMPCHOL_CHAIN")) chain = std::max(1, std::min(atoi(e), grid));
+  if (const char* e = getenv("BSPB200_LUMPCHOL_CHAIN")) chain = std::max(1, std::min(atoi(e), grid - 1));
   p.chainCtas = chain;
   ProfScope prof(st, KC_LUMP_CHOL, flops, 0);
   ensureDynSmem((const void*)lump_chol_kernel, kSmemBytes);
@@ -1042,7 +1124,7 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   // every CTA ends with one failing fetch of the regular ticket; the chain CTAs with one failing fetch of the diagonal one
   s.ticketBase += (unsigned)(regular + grid);
   s.arriveBase += (unsigned)grid;
-  s.diagBase += (unsigned)(p.nbc + std::min(chain, grid));
+  s.diagBase += (unsigned)(2 * p.nbc - 1 + std::min(chain, grid - 1));  // arrivals 1 .. chain fetch accumulate tickets
   return true;
 }
 

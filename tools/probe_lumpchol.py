@@ -46,28 +46,30 @@ for uf in ufs:
     got = api.debug_read(1, buf.ctypes.data_as(C.c_void_p), buf.nbytes)
     os.environ["BSPB200_LUMPCHOL_DBG"] = "0"
     st_ = buf[:64 * 16].reshape(64, 16)
-    segs = [("mainloop", 0, 1), ("stage_M_P", 1, 2), ("wait_W", 2, 3), ("trsm", 3, 4), ("store_L1+zeroS", 4, 5), ("syrk+D", 5, 7),
-            ("potrf", 7, 8), ("invert", 8, 9), ("W_store", 9, 10), ("L_store", 10, 11)]
+    # chain CTA (one SM: its clock64 stamps compare across steps): [0] step start, [3] M1 landed, [4] triangular product,
+    # [5] L1 staged + diagonal block zeroed + row copies issued, [7] D built + L1 published, [8] potrf, [9] L(d,d) stored +
+    # inverse, [10] W published + next operands requested. %globaltimer (ns): [1] operands of block d published by the
+    # accumulate job, [2] chain reaches block d, [12] W_d published. Accumulate jobs: [13] start, [14] main loop, [15] staged.
+    segs = [("wait_M1", 0, 3), ("trsm", 3, 4), ("stage_L1+zeroS", 4, 5), ("syrk+D+flag", 5, 7), ("potrf", 7, 8),
+            ("L_store+invert", 8, 9), ("W_publish+request", 9, 10)]
     nb = (n + 95) // 96
     rows = []
-    for d in range(1, min(nb, 64) - 1):
+    for d in range(2, min(nb, 63) - 1):
         s = st_[d]
-        if s[0] == 0:
-            continue
         rows.append([int(s[b_] - s[a_]) if s[b_] and s[a_] else 0 for _, a_, b_ in segs])
     rows = np.array(rows)
-    print("diag jobs:", len(rows))
-    print("phase (mean cycles over diag jobs):")
+    print("chain steps:", len(rows))
+    print("phase (mean cycles over the chain steps):")
     for i, (nm, _, _) in enumerate(segs):
-        print(f"  {nm:16s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
-    chain = rows[:, 3:9].sum(axis=1)
-    print("chain (trsm .. W_store): mean cycles", chain.mean(), "=", chain.mean() / 1.965e3, "us")
-    # W_d flag time differences between consecutive diag jobs = the realized chain step
-    w10 = st_[1:nb, 12]  # %globaltimer (ns) when W_d was published: the per-SM clock64 stamps do not compare across CTAs
-    w10 = w10[w10 > 0]
-    print("W flag to W flag: mean", np.diff(w10).mean() / 1e3, "us per block column (median", np.median(np.diff(w10)) / 1e3, ")")
-    sub = st_[2:nb - 1]
-    print("store_L1+zeroS split [x->E0, proxy fence, zero S, barrier+issue]:", [int((sub[:, b_] - sub[:, a_]).mean()) for a_, b_ in ((4, 13), (13, 14), (14, 15), (15, 5))])
+        print(f"  {nm:18s} {rows[:, i].mean():10.0f}   (min {rows[:, i].min()}, max {rows[:, i].max()})")
+    print("wait for the next operands per step (k cycles):", " ".join(str(int(x // 1000)) for x in rows[:, 6]))
+    s0 = st_[1:min(nb, 63), 0]
+    print("chain step (start to start): mean", np.diff(s0).mean(), "cycles =", np.diff(s0).mean() / 1.965e3, "us; median", np.median(np.diff(s0)))
+    slack = (st_[2:min(nb, 63), 2] - np.maximum(st_[2:min(nb, 63), 1], st_[2:min(nb, 63), 6])) / 1e3
+    print("M1 published after P (us), mean:", ((st_[2:min(nb, 63), 1] - st_[2:min(nb, 63), 6]) / 1e3).mean())
+    print("operands ready before the chain arrives (us): mean %.1f min %.1f, first blocks %s" % (slack.mean(), slack.min(), np.round(slack[:6], 1)))
+    acc = st_[2:min(nb, 63)]
+    print("accumulate jobs: main loop mean", int((acc[:, 14] - acc[:, 13]).mean()), "staging mean", int((acc[:, 15] - acc[:, 14]).mean()))
     ps = st_[63]
     print("potrf panel stamps (d = 20), panel 0:", [int(ps[i + 1] - ps[i]) for i in range(5)], "panel 1:", [int(ps[8 + i + 1] - ps[8 + i]) for i in range(5)],
           " [solve rows, barrier, warp-0 tile update, factor 8x8, barrier]")
