@@ -209,11 +209,102 @@ struct B200SymbolicCtx : SymbolicCtx {
       laneScratch.resize(tempBytesPerLane * lanes.size());
     }
   }
+  // ---- eager (source-driven) schedule of the wide lumps (round 2). The level-synchronous schedule above applies ALL the
+  // contributions to a lump when its level comes up: for the lumps at the top of the tree (one per level) that is a long
+  // serial run of GEMM + scatter pairs from sources that were finished many levels earlier (GRID 120x120: 15 of 25 ms).
+  // Here a contribution is issued as soon as its source level is done: into the targets of the NEXT level on the target's
+  // own lane (followed there by the target's factorization), into later targets on a low-priority background lane, so
+  // that only the contributions of a lump's last-finished children stay on its critical path. Dependencies are events
+  // per wide lump, there is no level barrier. Per target the order of the contributions is fixed (source level, then
+  // board order): deterministic.
+  struct EagerUpdate {
+    int64_t target, boardRow;
+  };
+  struct EagerPlan {
+    int64_t firstLump = -1;
+    std::vector<int32_t> level;                          // per lump (dense part)
+    std::vector<std::vector<EagerUpdate>> fromLevel;     // updates into WIDE targets by the level of their source
+    std::vector<int32_t> laneOf;                         // per lump: lane of a wide lump (position in its level)
+    std::vector<int32_t> evIndex;                        // per lump: index of its events, -1 for the small ones
+    std::vector<char> hasBg;                             // per lump: receives background contributions
+    int64_t numWide = 0;
+  };
+  std::unique_ptr<EagerPlan> eager;
+  std::vector<cudaEvent_t> evDone, evBg, evMain;
+  std::vector<Lane> bgLanes;
+  int numBgLanes = 16;
+  const EagerPlan& eagerPlan(int64_t firstLump, const WavePlan& wp) {
+    if (!eager || eager->firstLump != firstLump) {
+      auto e = std::make_unique<EagerPlan>();
+      const int64_t nLumps = skel.numLumps();
+      e->firstLump = firstLump;
+      e->level.assign(nLumps, 0), e->laneOf.assign(nLumps, 0), e->evIndex.assign(nLumps, -1), e->hasBg.assign(nLumps, 0);
+      for (int64_t l = firstLump; l < nLumps; l++) {
+        int32_t lv = 0;
+        for (int64_t r = skel.boardRowPtr[l], rEnd = skel.boardRowPtr[l + 1] - 1; r < rEnd; r++) {
+          const int64_t src = skel.boardColLump[r];
+          if (src >= firstLump) lv = std::max(lv, e->level[src] + 1);
+        }
+        e->level[l] = lv;
+      }
+      e->fromLevel.resize(wp.levels.size());
+      for (size_t lv = 0; lv < wp.levels.size(); lv++)
+        for (size_t i = 0; i < wp.levels[lv].bigLumps.size(); i++) {
+          const int64_t l = wp.levels[lv].bigLumps[i];
+          e->laneOf[l] = (int32_t)(i % std::max(1, numLanes));
+          e->evIndex[l] = (int32_t)e->numWide++;
+        }
+      // targets in level order (then index), per target its sources in board order: grouped by source level below
+      for (size_t lv = 0; lv < wp.levels.size(); lv++)
+        for (int64_t t : wp.levels[lv].bigLumps)
+          for (int64_t r = skel.boardRowPtr[t], rEnd = skel.boardRowPtr[t + 1] - 1; r < rEnd; r++) {
+            const int64_t src = skel.boardColLump[r];
+            if (src < firstLump) continue;
+            e->fromLevel[e->level[src]].push_back(EagerUpdate{t, r});
+            if (e->level[src] + 1 < (int32_t)lv) e->hasBg[t] = 1;
+          }
+      eager = std::move(e);
+    }
+    return *eager;
+  }
+  void ensureEager(const EagerPlan& e, size_t numLevels, size_t tempBytesPerLane) {
+    auto grow = [](std::vector<cudaEvent_t>& v, size_t n) {
+      while (v.size() < n) {
+        cudaEvent_t ev;
+        B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        v.push_back(ev);
+      }
+    };
+    grow(evDone, (size_t)e.numWide), grow(evBg, (size_t)e.numWide), grow(evMain, numLevels);
+    if (bgLanes.empty()) {
+      if (const char* env = getenv("BSPB200_BG_LANES")) numBgLanes = std::max(1, std::min(16, atoi(env)));
+      int lo = 0, hi = 0;
+      B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least urgent
+      bgLanes.resize(numBgLanes);
+      for (Lane& ln : bgLanes) {
+        B200_CUDA(cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, lo));
+        B200_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        ln.spanToChainOffset.resize(std::max<int64_t>(1, skel.numSpans()));
+      }
+    }
+    if (bgScratch.size() < tempBytesPerLane * bgLanes.size()) {
+      for (Lane& ln : bgLanes) B200_CUDA(cudaStreamSynchronize(ln.st));
+      bgScratch.resize(tempBytesPerLane * bgLanes.size());
+    }
+  }
+  DevBuf<unsigned char> bgScratch;
+
   ~B200SymbolicCtx() override {
     for (Lane& ln : lanes) {
       if (ln.st) cudaStreamDestroy(ln.st);
       if (ln.done) cudaEventDestroy(ln.done);
     }
+    for (Lane& ln : bgLanes) {
+      if (ln.st) cudaStreamDestroy(ln.st);
+      if (ln.done) cudaEventDestroy(ln.done);
+    }
+    for (auto* v : {&evDone, &evBg, &evMain})
+      for (cudaEvent_t ev : *v) cudaEventDestroy(ev);
     if (evLevel) cudaEventDestroy(evLevel);
   }
 
@@ -501,6 +592,14 @@ struct B200NumericCtx : NumericCtx<TT> {
       // the per-lump path for the wide ones
       const auto& wv = sym.wavePlan(firstSrc);
       Operand<T> all = opnd(m, 0);
+      {
+        static const bool timeline = getenv("BSPB200_PROFILE_TIMELINE") && atoi(getenv("BSPB200_PROFILE_TIMELINE")) != 0;
+        static const bool eagerOn = !getenv("BSPB200_EAGER") || atoi(getenv("BSPB200_EAGER")) != 0;
+        if (eagerOn && sym.numLanes > 1 && wv.host.numBig >= 2 && (!profileEnabled() || timeline)) {
+          fusedFactorEager(m, all, wv, firstSrc);
+          return;
+        }
+      }
       for (size_t lv = 0; lv < wv.host.levels.size(); lv++) {
         const WaveLevel& L = wv.host.levels[lv];
         waveUpdate<T>(sym.stream, m.batch, all, wv.tiles.ptr() + L.tileBegin, L.tileEnd - L.tileBegin,
@@ -548,6 +647,95 @@ struct B200NumericCtx : NumericCtx<TT> {
     }
   }
 
+  // the eager schedule (see B200SymbolicCtx::EagerPlan)
+  void fusedFactorEager(const Mats<T>& m, Operand<T> all, const typename B200SymbolicCtx::DevWave& wv, int64_t firstSrc) {
+    const auto& E = sym.eagerPlan(firstSrc, wv.host);
+    const size_t nLevels = wv.host.levels.size();
+    sym.ensureLanes(m.batch, laneTempBytes());
+    sym.ensureEager(E, nLevels, laneTempBytes());
+    const int nNear = (int)sym.lanes.size(), nBg = (int)sym.bgLanes.size();
+    auto ctxOf = [&](int q) {  // q < nNear: lane, else background lane
+      if (q < nNear) return laneCtx(q);
+      LaneCtx lc;
+      const int b = q - nNear;
+      lc.st = sym.bgLanes[b].st;
+      lc.temp.base = (T*)(sym.bgScratch.ptr() + (size_t)b * laneTempBytes());
+      lc.temp.stride = tempSize;
+      lc.spanToChainOffset = sym.bgLanes[b].spanToChainOffset.ptr();
+      return lc;
+    };
+    // everything queued on the solver's stream so far (the sparse elimination) precedes the lanes
+    B200_CUDA(cudaEventRecord(sym.evLevel, sym.stream));
+    for (int q = 0; q < nNear + nBg; q++) B200_CUDA(cudaStreamWaitEvent(ctxOf(q).st, sym.evLevel, 0));
+    // background lane of a target: by its LEVEL first (a stream is a FIFO: contributions into far targets queued ahead
+    // of those into the level that comes up next would hold that level back), then by its position in the level
+    auto bgOf = [&](int64_t t) {
+      const int perLevel = nBg >= 8 ? 2 : 1, nl = std::max(1, nBg / perLevel);
+      return (E.level[t] % nl) * perLevel + E.laneOf[t] % perLevel;
+    };
+    std::vector<int64_t> prepared(nNear + nBg, -1);   // target whose span-to-chain table the stream holds
+    std::vector<int64_t> waited;                      // (stream, event index) pairs already waited for in this level
+    std::vector<char> mainWaited(E.numWide, 0);
+    for (size_t lv = 0; lv < nLevels; lv++) {
+      const WaveLevel& L = wv.host.levels[lv];
+      bool mainWork = false;
+      if (L.tileEnd > L.tileBegin || L.panelEnd > L.panelBegin) {
+        // the small lumps of the level (solver's stream) take contributions from every earlier source
+        for (size_t pl = 0; pl < lv; pl++)
+          for (int64_t b : wv.host.levels[pl].bigLumps)
+            if (!mainWaited[E.evIndex[b]]) {
+              B200_CUDA(cudaStreamWaitEvent(sym.stream, sym.evDone[E.evIndex[b]], 0));
+              mainWaited[E.evIndex[b]] = 1;
+            }
+        waveUpdate<T>(sym.stream, m.batch, all, wv.tiles.ptr() + L.tileBegin, L.tileEnd - L.tileBegin, wv.targets.ptr(),
+                      wv.sources.ptr(), wv.rowMap.ptr());
+        potrfTrsmPanelBatch<T>(sym.stream, m.batch, all, wv.panels.ptr() + L.panelBegin, L.panelEnd - L.panelBegin,
+                               L.numSmall, wv.panelFlops[lv]);
+        B200_CUDA(cudaEventRecord(sym.evMain[lv], sym.stream));
+        mainWork = true;
+      }
+      // the wide lumps of the level: every contribution is already queued on their lane
+      for (int64_t l : L.bigLumps) {
+        LaneCtx lc = laneCtx(E.laneOf[l]);
+        factorLumpColumn(m, l, &lc);
+        B200_CUDA(cudaEventRecord(sym.evDone[E.evIndex[l]], lc.st));
+      }
+      // contributions of this level's lumps: next-level targets first (their lanes), then the background
+      waited.clear();
+      for (int pass = 0; pass < 2; pass++)
+        for (const auto& u : E.fromLevel[lv]) {
+          const int64_t t = u.target, src = skel.boardColLump[u.boardRow];
+          const bool near = E.level[t] == (int32_t)lv + 1;
+          if (near != (pass == 0)) continue;
+          const int q = near ? E.laneOf[t] : nNear + bgOf(t);
+          LaneCtx lc = ctxOf(q);
+          if (near && E.hasBg[t] && prepared[q] != t) {
+            // first near contribution of t: its background contributions (all queued by now) come first
+            const int qb = nNear + bgOf(t);
+            B200_CUDA(cudaEventRecord(sym.evBg[E.evIndex[t]], ctxOf(qb).st));
+            B200_CUDA(cudaStreamWaitEvent(lc.st, sym.evBg[E.evIndex[t]], 0));
+          }
+          const int64_t evKey = (int64_t)q * (E.numWide + 1) + (E.evIndex[src] >= 0 ? E.evIndex[src] : E.numWide);
+          if (std::find(waited.begin(), waited.end(), evKey) == waited.end()) {
+            if (E.evIndex[src] >= 0) B200_CUDA(cudaStreamWaitEvent(lc.st, sym.evDone[E.evIndex[src]], 0));
+            else if (mainWork) B200_CUDA(cudaStreamWaitEvent(lc.st, sym.evMain[lv], 0));
+            waited.push_back(evKey);
+          }
+          if (prepared[q] != t) {
+            const int64_t begin = skel.chainColPtr[t];
+            b200::prepareAssemble(lc.st, sym.dsk, lc.spanToChainOffset, begin, skel.chainColPtr[t + 1] - begin);
+            prepared[q] = t;
+          }
+          updateOne(m, t, u.boardRow, lc.st, lc.spanToChainOffset, lc.temp);
+        }
+    }
+    for (int q = 0; q < nNear + nBg; q++) {
+      cudaEvent_t ev = q < nNear ? sym.lanes[q].done : sym.bgLanes[q - nNear].done;
+      B200_CUDA(cudaEventRecord(ev, ctxOf(q).st));
+      B200_CUDA(cudaStreamWaitEvent(sym.stream, ev, 0));
+    }
+  }
+
   // where one lump column's chain of kernels runs: the solver's stream and shared workspaces, or a lane
   struct LaneCtx {
     cudaStream_t st;
@@ -578,20 +766,25 @@ struct B200NumericCtx : NumericCtx<TT> {
         b200::prepareAssemble(st, sym.dsk, s2c, begin, skel.chainColPtr[l + 1] - begin);
         prepared = true;
       }
-      const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
-      const int64_t k = skel.lumpSize(src);
-      const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
-      const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
-      const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
-      const int64_t rowsInBoard = skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin;
-      const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
-      BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
-      Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
-      const Work<T> tmp = lc ? lc->temp : temp();
-      gemmNT<T>(st, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(tmp, 0), rowsInBoard, false);
-      b200::assemble<T>(st, m.batch, sym.dsk, s2c, m, tmp, rowBegin, skel.lumpSize(l), cb + ch0, rowsInBoard,
-                        chEnd - ch0, ch1 - ch0, rowsToEnd);
+      updateOne(m, l, r, st, s2c, lc ? lc->temp : temp());
     }
+  }
+
+  // contribution of the source lump of board row r into lump l: GEMM into the temp + scatter
+  void updateOne(const Mats<T>& m, int64_t l, int64_t r, cudaStream_t st, int64_t* s2c, const Work<T>& tmp) {
+    const int64_t src = skel.boardColLump[r];
+    const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
+    const int64_t k = skel.lumpSize(src);
+    const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
+    const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
+    const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
+    const int64_t rowsInBoard = skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin;
+    const int64_t rowsToEnd = skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin;
+    BASPACHO_CHECK_LE(rowsInBoard * rowsToEnd, tempSize);
+    Operand<T> B = opnd(m, skel.chainData[cb + ch0]);
+    gemmNT<T>(st, m.batch, rowsToEnd, rowsInBoard, k, T(1), B, k, B, k, T(0), opnd(tmp, 0), rowsInBoard, false);
+    b200::assemble<T>(st, m.batch, sym.dsk, s2c, m, tmp, rowBegin, skel.lumpSize(l), cb + ch0, rowsInBoard, chEnd - ch0,
+                      ch1 - ch0, rowsToEnd);
   }
 
   void factorLumpColumn(const Mats<T>& m, int64_t l, const LaneCtx* lc = nullptr) {

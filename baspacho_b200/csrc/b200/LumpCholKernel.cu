@@ -31,7 +31,11 @@
 #include <cuda.h>
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <stdexcept>
+#include <tuple>
+#include <vector>
 #include "B200Kernels.h"
 
 namespace BaSpaCho {
@@ -64,15 +68,16 @@ struct LcParams {
   int64_t ld;
   int n, rows;          // lump width, total rows (n + rowsBelow)
   int nbc, nbr;         // block columns / block rows
-  int numRegular;       // off-diagonal tiles that are not the sub-diagonal partner of a diagonal block
-  int chainCtas;        // the first chainCtas CTAs to arrive work through the diagonal jobs, in order
+  int numJobs;          // entries of `jobs`
+  const int4* jobs;     // the job list in ticket order: {i, c, k0 | seg << 20, k1 | type << 28 | last << 30}
   unsigned* done;       // [nbr * nbc] tile flags (epoch valued)
+  unsigned* seg;        // [nbr * nbc] segments of the tile's sum applied so far (epoch * 256 + count)
   unsigned* wdone;      // [nbc] inverse flags
   unsigned* mdone;      // [nbc] flags of the accumulated operands of the diagonal blocks (mbuf): M1 ..
   unsigned* pdone;      // .. and P
   double* mbuf;         // [nbc][kMbufDoubles]: M1 = A(d,d-1) - sum ([96][LDE]) and P = A(d,d) - sum (78 packed 8 x 8 tiles)
-  unsigned* ctr;        // [0] ticket of the regular jobs, [2] arrival counter, [3] ticket of the diagonal jobs (never reset)
-  unsigned ticketBase, arriveBase, diagBase;
+  unsigned* ctr;        // [0] job ticket, [2] arrival counter (never reset)
+  unsigned ticketBase, arriveBase;
   unsigned* abortFlag;  // holds the epoch of the launch that timed out (never reset)
   double* wbuf;         // [nbc][96 * LDE] block inverses, row-major, padded rows: the epilogue's operand layout as it is
   unsigned epoch;
@@ -147,6 +152,20 @@ __device__ __forceinline__ double rsqrtNewton(double x) {  // see DenseKernels.c
   return y;
 }
 
+// bounded wait for a flag to reach `value` (abort word compared with `epoch`)
+__device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned value, unsigned* abortFlag, unsigned epoch) {
+  unsigned spins = 0;
+  while (ldAcquire(flag) != value) {
+    if ((++spins & 63u) == 0) {
+      if (*(volatile unsigned*)abortFlag == epoch) return false;
+      if (spins > (1u << 24)) {
+        atomicExch(abortFlag, epoch);
+        return false;
+      }
+    }
+  }
+  return true;
+}
 // bounded wait for a flag to reach `epoch`; returns false after the abort flag was raised (by us or anybody)
 __device__ __forceinline__ bool waitFlag(const unsigned* flag, unsigned epoch, unsigned* abortFlag) {
   unsigned spins = 0;
@@ -437,20 +456,12 @@ __device__ __forceinline__ void invertTile(const double* S, double* Wm, double* 
 // depend on smaller tickets: no deadlock whatever the number of co-resident CTAs, as long as chain CTAs are the first to
 // arrive (they are resident by construction).
 struct Job {
-  int i, c, diag;  // diag: this job also owns the diagonal tile (i, i)
+  int i, c;     // tile (block row, block column); for P = (d, d) of the chain: i = d, c = d - 1
+  int k0, k1;   // K blocks [k0, k1) of the tile's sum
+  int seg;      // index of this segment among the tile's segments
+  int diag;     // 0: regular tile, 1: M1 = (d, d-1), 2: P = (d, d)
+  int last;     // the segment that finishes the tile (triangular product / hand-over to the chain)
 };
-__device__ __forceinline__ int firstRegularRow(int c, int nbc) { return c + 1 < nbc ? c + 2 : c + 1; }
-__device__ __forceinline__ Job decodeRegular(int t, int nbc, int nbr) {
-  Job j;
-  int rem = t, c = 0;
-  for (;;) {
-    const int cnt = max(0, nbr - firstRegularRow(c, nbc));
-    if (rem < cnt) break;
-    rem -= cnt, c++;
-  }
-  j.c = c, j.i = firstRegularRow(c, nbc) + rem, j.diag = 0;
-  return j;
-}
 
 // what the producer lane needs to request the operand tiles of a job
 struct LoadCtx {
@@ -467,7 +478,7 @@ __device__ __forceinline__ void issueStage(LoadCtx& lc, int kt, unsigned q, uint
                                            uint32_t emptyBar0) {
   const unsigned stage = q % NST, parity = (q / NST) & 1;
   mbarWait(emptyBar0 + 8 * stage, parity ^ 1);  // every warp released the previous use of the slot
-  if (kt % (TB / BK) == 0 && lc.ok) {           // first stage of a K block: its two source tiles must be published
+  if (kt % (TB / BK) == 0 && lc.ok) {           // first stage of a K block (segments start on one): its two source tiles must be published
     const int kb = kt / (TB / BK);
     const long long t0 = clock64();
     lc.ok = waitFlag(lc.doneA + kb, lc.epoch, lc.abortFlag) && waitFlag(lc.doneB + kb, lc.epoch, lc.abortFlag);
@@ -482,16 +493,17 @@ __device__ __forceinline__ void issueStage(LoadCtx& lc, int kt, unsigned q, uint
 }
 
 template <int TN>  // column tiles per warp: 6 (one 96-wide tile, warps 4 x 2 of 24 x 48) or 12 (two tiles, 24 x 96)
-__device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int kTiles, uint32_t stagesBase, uint32_t fullBar0,
-                                         uint32_t emptyBar0, unsigned& it, int rowA, int rowB, int g, int t, int lane,
-                                         bool producer, LoadCtx& lc) {
+__device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int ktBegin, int ktEnd, uint32_t stagesBase,
+                                         uint32_t fullBar0, uint32_t emptyBar0, unsigned& it, int rowA, int rowB, int g, int t,
+                                         int lane, bool producer, LoadCtx& lc) {
   // swizzled position of this lane's fragment element inside a 128-byte row: 16-byte chunk (k >> 1) ^ (row & 7)
   uint32_t koff[BK / 4];
 #pragma unroll
   for (int s = 0; s < BK / 4; s++) koff[s] = ((uint32_t)(((2 * s) | (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
   if (producer)
-    for (int kt = 0; kt < NST - 1 && kt < kTiles; kt++) issueStage(lc, kt, it + kt, stagesBase, fullBar0, emptyBar0);
-  for (int kt = 0; kt < kTiles; kt++, it++) {
+    for (int kt = ktBegin; kt < ktBegin + NST - 1 && kt < ktEnd; kt++)
+      issueStage(lc, kt, it + (kt - ktBegin), stagesBase, fullBar0, emptyBar0);
+  for (int kt = ktBegin; kt < ktEnd; kt++, it++) {
     const unsigned stage = it % NST, parity = (it / NST) & 1;
     mbarWait(fullBar0 + 8 * stage, parity);
     const uint32_t as = stagesBase + stage * kStageBytes + (uint32_t)(rowA + g) * 128;
@@ -513,7 +525,7 @@ __device__ __forceinline__ void mainLoop(double (&acc)[3][12][2], int kTiles, ui
     __syncwarp();
     if (lane == 0) mbarArrive(emptyBar0 + 8 * stage);
     // the slot of iteration kt - 1 is requested again for iteration kt + NST - 1
-    if (producer && kt + NST - 1 < kTiles) issueStage(lc, kt + NST - 1, it + NST - 1, stagesBase, fullBar0, emptyBar0);
+    if (producer && kt + NST - 1 < ktEnd) issueStage(lc, kt + NST - 1, it + NST - 1, stagesBase, fullBar0, emptyBar0);
     __syncwarp();
   }
 }
@@ -609,9 +621,8 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   if (tid == 0) chainS = (int)(atomicAdd(p.ctr + 2, 1u) - p.arriveBase);
   __syncthreads();
   const int arrival = chainS;
-  // arrival 0: THE chain CTA (serial part of every diagonal block); arrivals 1 .. chainCtas: accumulate the operands of
-  // the diagonal blocks ahead of it; everybody else (and those, once they run out of their own work): regular tiles
-  bool chain = arrival >= 1 && arrival <= p.chainCtas;
+  // arrival 0: THE chain CTA (serial part of every diagonal block; once through, it joins the others); everybody else
+  // works through the job list
   if (arrival == 0) {
     // ================================================================================ the chain of diagonal blocks
     // Step d:  L1 = L(d,d-1) = M1 W_{d-1}^T  ->  D = P - L1 L1^T  ->  potrf(D)  ->  W_d = L(d,d)^-1, with W_{d-1} still in
@@ -801,41 +812,32 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
   }
 
   for (;;) {
+    if (tid == 0) jobS = (int)(atomicAdd(p.ctr, 1u) - p.ticketBase);
+    __syncthreads();
+    const int jt = jobS;
+    if (jt >= p.numJobs) break;
     Job job;
-    if (chain) {
-      if (tid == 0) jobS = (int)(atomicAdd(p.ctr + 3, 1u) - p.diagBase);
-      __syncthreads();
-      const int dj = jobS;
-      __syncthreads();
-      if (dj >= 2 * p.nbc - 1) {  // every accumulate job is taken: help with the regular tiles
-        chain = false;
-        continue;
-      }
-      // ticket 0: P of block 0; then, for d = 1, 2, ..: M1 of block d (diag = 1), P of block d (diag = 2)
-      const int dd = (dj + 1) >> 1;
-      job.i = dd, job.c = dd - 1, job.diag = dj == 0 ? 2 : 1 + ((dj + 1) & 1);
-    } else {
-      if (tid == 0) jobS = (int)(atomicAdd(p.ctr, 1u) - p.ticketBase);
-      __syncthreads();
-      const int jt = jobS;
-      if (jt >= p.numRegular) break;
-      job = decodeRegular(jt, p.nbc, p.nbr);
+    {
+      const int4 q = __ldg(p.jobs + jt);
+      job.i = q.x, job.c = q.y, job.k0 = q.z, job.k1 = q.w & 0xfffffff, job.diag = (q.w >> 28) & 3, job.last = (q.w >> 30) & 1;
+      job.seg = (int)((unsigned)q.z >> 20);
+      job.k0 &= 0xfffff;
     }
     const int c = job.c, bi = job.i;
-    const int kTiles = c > 0 ? c * (TB / BK) : 0;  // K = 96 c
     // block row of the B operand: c for a tile (i, c) - regular tiles and M1 = (d, d-1) -, d itself for P = (d, d)
     const int browB = job.diag == 2 ? bi : (c < 0 ? 0 : c);
     const int rowA0 = bi * TB, rowB0 = browB * TB;
+    // this tile's own column block in A and its valid extent
+    const int ownCol = job.diag == 2 ? bi : c;
+    unsigned* segFlag = p.seg + (int64_t)bi * p.nbc + ownCol;
 
     const long long tJob = clock64();
     LC_STAMP(13)
-    if (c >= 0 || job.diag) {
-      // the tiles' own (original) entries are only needed after the K loop: pull them into L2 now, one 128-byte line
-      // per request, so that the epilogue does not wait for HBM (diagonal jobs measured ~10 us there, on the chain)
-      const int cols0 = (job.diag == 2 ? bi : (c >= 0 ? c : 0)) * TB;
+    {
+      // the tile's own entries are only needed after the K loop: pull them into L2 now, one 128-byte line per request
       for (int idx = tid; idx < TB * 6; idx += kConsumers) {
         const int r = idx / 6, l = idx % 6;
-        const int64_t gr = (int64_t)rowA0 + r, gc = (int64_t)cols0 + l * 16;
+        const int64_t gr = (int64_t)rowA0 + r, gc = (int64_t)ownCol * TB + l * 16;
         if (gr < p.rows && gc < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + gr * ld + gc));
       }
     }
@@ -849,16 +851,53 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     lc.abortFlag = p.abortFlag, lc.epoch = p.epoch, lc.rowA0 = rowA0, lc.rowB0 = rowB0, lc.nBTiles = 1;
     lc.ok = *(volatile unsigned*)p.abortFlag != p.epoch;
     lc.waitCycles = 0;
-    mainLoop<6>(acc, kTiles, stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane, producer, lc);
+    mainLoop<6>(acc, job.k0 * (TB / BK), job.k1 * (TB / BK), stagesBase, fullBar0, emptyBar0, it, 24 * wm, 48 * wn, g, t, lane,
+                producer, lc);
+    // an earlier segment of this tile's sum has to have landed in the tile before it is read below
+    if (tid == 0 && job.seg > 0 && lc.ok) {
+      const long long t0 = clock64();
+      waitFlag(segFlag, p.epoch * 256u + (unsigned)job.seg, p.abortFlag, p.epoch);
+      lc.waitCycles += clock64() - t0;
+    }
     __syncthreads();  // (A) every stage has been consumed: the stage memory becomes the epilogue workspace
     const long long tMain = clock64();
     cycWait += lc.waitCycles;
     LC_STAMP(14)
 
     const int nc = c >= 0 ? min(TB, p.n - c * TB) : 0;  // valid columns of block column c
+    if (!job.last) {
+      // ---- a segment of the tile's sum: A(tile) -= acc, in place (only the lower 8 x 8 tiles of a diagonal block: the
+      // entries above its diagonal are never written)
+      const int rbase = 24 * wm, cbase = 48 * wn;
+      const int ncOwn = min(TB, p.n - ownCol * TB);
+      double2 av[3][6];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const bool on = rowA0 + r < p.rows && cc < ncOwn && (job.diag != 2 || 6 * wn + j <= 3 * wm + i);
+          av[i][j] = make_double2(0.0, 0.0);
+          if (on) av[i][j] = __ldcg(reinterpret_cast<const double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)ownCol * TB + cc));
+        }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
+          const bool on = rowA0 + r < p.rows && cc < ncOwn && (job.diag != 2 || 6 * wn + j <= 3 * wm + i);
+          if (on)
+            __stcg(reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)ownCol * TB + cc),
+                   make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]));
+        }
+      __syncthreads();
+      if (tid == 0) stRelease(segFlag, p.epoch * 256u + (unsigned)job.seg + 1u);
+      __syncthreads();  // (B)
+      cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
+      continue;
+    }
     // W_c -> E1 by one bulk copy (the buffer holds the padded operand layout). Requested right away when W_c is already
-    // published - the copy then runs under the staging below - else after the staging: a thread that spins on the flag
-    // first would hold back its share of the staging, which for a diagonal job sits on the chain.
+    // published - the copy then runs under the staging below - else after the staging
     bool wIssued = false;
     auto requestW = [&](bool block) {
       if (wIssued || c < 0) return;
@@ -978,6 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
     __syncthreads();  // (B)
     cycMain += tMain - tJob, cycEpi += clock64() - tMain, nJobs++;
   }
+
 #undef LC_STAMP
   if (p.dbg && tid == 0) {
     long long* q = p.dbg + 64 * 16 + (int64_t)blockIdx.x * 4;
@@ -1014,8 +1054,62 @@ struct LcState {
   DevBuf<double> wbuf, mbuf;
   int nbcCap = 0;
   int64_t tileCap = 0;
-  unsigned epoch = 0, ticketBase = 0, arriveBase = 0, diagBase = 0;
+  unsigned epoch = 0, ticketBase = 0, arriveBase = 0;
+  // job lists by shape (block columns, block rows, segment length): built and uploaded once per stream and shape
+  struct JobList {
+    DevBuf<int4> dev;
+    int64_t count = 0;
+  };
+  std::map<std::tuple<int, int, int>, std::unique_ptr<JobList>> jobLists;
 };
+
+// The job list of a shape. Every tile's sum over K blocks [0, K) is cut into segments of ~seglen blocks with staggered
+// boundaries; a segment that does not finish the tile is applied to the tile in place. Ticket order: by the LAST K block
+// a job needs (= the chain step that makes it runnable), inside that the hand-overs to the chain first, then the jobs
+// that finish a tile, then the rest, nearest column first. A job only depends on jobs with a smaller key (the previous
+// segment of its tile, the finishing jobs of the tiles it reads) and on the chain CTA, which in turn only waits for
+// hand-over jobs with smaller keys: whatever the number of resident CTAs, the job with the smallest ticket still
+// running can always finish. Without the segments a CTA held a tile from its first K block to its last, and in the
+// first third of the run - when tiles can only advance one K block per chain step - nearly every CTA sat waiting with
+// one tile while a thousand other tiles could have used the same K block (round 2b: 20 % of the CTA time in waits).
+std::vector<int4> buildJobs(int nbc, int nbr, int seglen, int lag) {
+  struct J {
+    int key, rank, c, i, k0, k1, seg, type, last;
+  };
+  std::vector<J> js;
+  auto addTile = [&](int i, int c, int type) {
+    const int K = std::max(0, c);  // K blocks of the sum (c = d - 1 for the two tiles of diagonal block d)
+    int b = K > 0 ? ((i * 7 + c * 3) % seglen) + 1 : 0, k0 = 0, seg = 0;
+    for (;;) {
+      int k1 = std::min(K, b);
+      if (K - k1 < std::max((seglen + 1) / 2, lag + 1)) k1 = K;  // no short tail segment (and room for the lag below)
+      const int last = k1 == K;
+      const int rank = type != 0 ? (last ? 0 : 1) : (last ? 2 : 3);
+      // a segment that does not finish its tile is not urgent: it takes its ticket `lag` chain steps after it became
+      // runnable, behind the jobs the chain is waiting for (still before the tile's next segment / finishing job)
+      js.push_back(J{last ? k1 : k1 + lag, rank, c, i, k0, k1, seg, type, last});
+      if (last) break;
+      k0 = k1, b = k1 + seglen, seg++;
+    }
+  };
+  for (int d = 0; d < nbc; d++) {
+    if (d > 0) addTile(d, d - 1, 1);
+    addTile(d, d - 1, 2);
+  }
+  for (int c = 0; c < nbc; c++)
+    for (int i = (c + 1 < nbc ? c + 2 : c + 1); i < nbr; i++) addTile(i, c, 0);
+  std::stable_sort(js.begin(), js.end(), [](const J& a, const J& b) {
+    return std::make_tuple(a.key, a.rank, a.c, a.i) < std::make_tuple(b.key, b.rank, b.c, b.i);
+  });
+  std::vector<int4> out;
+  out.reserve(js.size());
+  for (const J& j : js) {
+    if (j.seg > 255 || j.k1 >= (1 << 20)) throw std::runtime_error("lump_chol: job list out of range");
+    out.push_back(make_int4(j.i, j.c, j.k0 | (j.seg << 20), j.k1 | (j.type << 28) | (j.last << 30)));
+  }
+  return out;
+}
+
 long long*& lastDbg() {
   static long long* p = nullptr;
   return p;
@@ -1058,28 +1152,45 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   LcParams p;
   p.A = A, p.ld = ld, p.n = (int)n, p.rows = (int)(n + rowsBelow);
   p.nbc = ceilDiv(n, TB), p.nbr = ceilDiv(n + rowsBelow, TB);
-  int64_t regular = 0;
-  for (int c = 0; c < p.nbc; c++) regular += std::max(0, p.nbr - (c + 1 < p.nbc ? c + 2 : c + 1));
-  p.numRegular = (int)regular;
-  const int64_t jobs = regular + 2 * p.nbc - 1;
-
   LcState& s = lcState(st);
   const int64_t tiles = (int64_t)p.nbr * p.nbc;
   if (p.nbc > s.nbcCap || tiles > s.tileCap) {
     B200_CUDA(cudaStreamSynchronize(st));
     s.nbcCap = std::max(p.nbc, s.nbcCap * 2);
     s.tileCap = std::max(tiles, s.tileCap * 2);
-    s.words.resize((size_t)(4 + 3 * s.nbcCap + s.tileCap));
+    s.words.resize((size_t)(4 + 3 * s.nbcCap + 2 * s.tileCap));
     s.wbuf.resize((size_t)s.nbcCap * TB * LDE);
     s.mbuf.resize((size_t)s.nbcCap * kMbufDoubles);
     B200_CUDA(cudaMemsetAsync(s.words.ptr(), 0, s.words.size() * sizeof(unsigned), st));
-    s.epoch = 0, s.ticketBase = s.arriveBase = s.diagBase = 0;
+    s.epoch = 0, s.ticketBase = s.arriveBase = 0;
   }
   p.ctr = s.words.ptr(), p.abortFlag = s.words.ptr() + 1, p.wdone = s.words.ptr() + 4;
   p.mdone = s.words.ptr() + 4 + s.nbcCap, p.pdone = s.words.ptr() + 4 + 2 * s.nbcCap;
-  p.done = s.words.ptr() + 4 + 3 * s.nbcCap;
+  p.done = s.words.ptr() + 4 + 3 * s.nbcCap, p.seg = p.done + s.tileCap;
   p.wbuf = s.wbuf.ptr(), p.mbuf = s.mbuf.ptr();
-  p.epoch = ++s.epoch, p.ticketBase = s.ticketBase, p.arriveBase = s.arriveBase, p.diagBase = s.diagBase;
+  p.epoch = ++s.epoch, p.ticketBase = s.ticketBase, p.arriveBase = s.arriveBase;
+  // segment length: BSPB200_LUMPCHOL_SEG (K blocks of 96; 0 = whole sums, one job per tile: the default); at most 255
+  // segments a tile. Measured on the 5226-wide lump (profiles/README.md): whole sums 2.28 ms; segments of 2 / 4 / 8 / 16 /
+  // 24 K blocks 3.01 / 2.72 / 2.58 / 2.51 / 2.46 ms (every extra job costs ~20 k cycles of pipeline ramp, read-modify-
+  // write of the tile and flag waits, and the flood of early segments holds back the jobs the chain waits for; giving
+  // the segments a later ticket - BSPB200_LUMPCHOL_LAG - recovers little: 8/3 2.57, 8/6 2.54, 16/4 2.50 ms).
+  int seglen = 0;
+  if (const char* e = getenv("BSPB200_LUMPCHOL_SEG")) seglen = atoi(e);
+  if (seglen <= 0) seglen = 1 << 20;
+  seglen = std::max(seglen, p.nbc / 200 + 1);
+  int lag = 0;
+  if (const char* e = getenv("BSPB200_LUMPCHOL_LAG")) lag = std::max(0, atoi(e));
+  auto& jl = s.jobLists[std::make_tuple(p.nbc, p.nbr, seglen * 64 + lag)];
+  if (!jl) {
+    jl = std::make_unique<LcState::JobList>();
+    const std::vector<int4> host = buildJobs(p.nbc, p.nbr, seglen, lag);
+    jl->count = (int64_t)host.size();
+    jl->dev.resize(host.size());
+    B200_CUDA(cudaMemcpyAsync(jl->dev.ptr(), host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaStreamSynchronize(st));  // `host` goes out of scope
+  }
+  p.jobs = jl->dev.ptr(), p.numJobs = (int)jl->count;
+  const int64_t jobs = jl->count;
   p.dbg = nullptr;
   if (const char* e = getenv("BSPB200_LUMPCHOL_DBG")) {
     if (atoi(e) != 0) {
@@ -1113,18 +1224,13 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   if (const char* e = getenv("BSPB200_LUMPCHOL_GRID")) want = atoi(e);
   // at least two CTAs: the chain CTA only consumes what the accumulate jobs of the others publish
   const int grid = (int)std::max<int64_t>(2, std::min<int64_t>({(int64_t)sms, jobs + 1, std::max<int64_t>(want, 16)}));
-  // chain CTAs: a diagonal job needs ~0.4 chain steps of accumulation per block column it has behind it
-  int chain = std::max(1, std::min((int)(0.4 * p.nbc) + 1, std::max(1, grid / 3)));
-  if (const char* e = getenv("BSPB200_LUMPCHOL_CHAIN")) chain = std::max(1, std::min(atoi(e), grid - 1));
-  p.chainCtas = chain;
   ProfScope prof(st, KC_LUMP_CHOL, flops, 0);
   ensureDynSmem((const void*)lump_chol_kernel, kSmemBytes);
   lump_chol_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p);
   B200_LAUNCH_CHECK();
-  // every CTA ends with one failing fetch of the regular ticket; the chain CTAs with one failing fetch of the diagonal one
-  s.ticketBase += (unsigned)(regular + grid);
+  // every CTA ends with one failing fetch of the ticket
+  s.ticketBase += (unsigned)(jobs + grid);
   s.arriveBase += (unsigned)grid;
-  s.diagBase += (unsigned)(2 * p.nbc - 1 + std::min(chain, grid - 1));  // arrivals 1 .. chain fetch accumulate tickets
   return true;
 }
 
