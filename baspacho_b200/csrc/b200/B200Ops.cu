@@ -118,6 +118,8 @@ struct B200SymbolicCtx : SymbolicCtx {
     e->lightList.upload(p.lightList), e->heavyList.upload(p.heavyList);
     d.lightList = e->lightList.ptr(), d.heavyList = e->heavyList.ptr();
     d.numLight = (int64_t)p.lightList.size(), d.numHeavy = (int64_t)p.heavyList.size();
+    d.lightTasks = 0;
+    for (int32_t dl : p.lightList) d.lightTasks += p.dstTaskPtr[dl + 1] - p.dstTaskPtr[dl];
     d.dstOff = e->dstOff.ptr(), d.dstStride = e->dstStride.ptr(), d.dstRows = e->dstRows.ptr();
     d.dstCols = e->dstCols.ptr(), d.dstTaskPtr = e->dstTaskPtr.ptr(), d.taskA = e->taskA.ptr();
     d.taskB = e->taskB.ptr(), d.taskK = e->taskK.ptr();

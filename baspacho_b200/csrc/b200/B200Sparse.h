@@ -37,6 +37,7 @@ struct DevElimPlan {
   const int32_t* lightList;
   const int32_t* heavyList;
   int64_t numLight, numHeavy;
+  int64_t lightTasks;  // pair tasks of the light destinations
   const int64_t* dstOff;
   const int32_t* dstStride;
   const int16_t* dstRows;

@@ -2,6 +2,7 @@
 // pseudo factor, elimination-range triangular solves and the vector gather/scatter of the dense solves.
 // These are HBM-bound index-driven kernels: no tensor cores, coalesced row-wise accesses, fixed summation
 // order (deterministic, no atomics - unlike reference MatOpsCuda.cu:235-331, 883-1012).
+#include <type_traits>
 #include "B200Sparse.h"
 
 namespace BaSpaCho {
@@ -214,6 +215,158 @@ __global__ void __launch_bounds__(LANES > 32 ? LANES : 128)
 #pragma unroll
     for (int e = 0; e < NR * NC; e++)
       if (e % LANES == sub) dst[(e / NC) * stride + (e % NC)] -= acc[e];
+  }
+}
+
+// The per-lane gather with 16-byte operand loads (round 2). A block starts on an 8-byte boundary only: an even element
+// offset is 16-byte aligned and is read as NE/2 double2, an odd one as one double + (NE-2)/2 double2 + one double. The
+// two cases are separate straight-line paths (lanes of a warp may take either: both run, each with its lanes) that fill
+// the same registers with static indices - the parity-SELECT formulation of round 1 (load 20, pick 18) cost 36 selects
+// per block and 164 registers. Halves the L1 sector accesses per task (36 -> 18..20), which bound the 8-byte version
+// (ncu r02: 261 M sectors, 0.96 per cycle and SM). Same task ownership and summation order as the plain kernel.
+template <typename T, int NE>
+__device__ __forceinline__ void loadBlockVec(T (&v)[NE], const T* __restrict__ src) {
+  static_assert(sizeof(T) == 8 && NE % 2 == 0, "double blocks with an even element count");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < NE / 2; i++) {
+      const double2 q = __ldg(reinterpret_cast<const double2*>(src) + i);
+      v[2 * i] = q.x, v[2 * i + 1] = q.y;
+    }
+  } else {
+    v[0] = __ldg(src);
+#pragma unroll
+    for (int i = 0; i < NE / 2 - 1; i++) {
+      const double2 q = __ldg(reinterpret_cast<const double2*>(src + 1) + i);
+      v[1 + 2 * i] = q.x, v[2 + 2 * i] = q.y;
+    }
+    v[NE - 1] = __ldg(src + NE - 1);
+  }
+}
+template <int NR, int NC, int K, int LANES>
+__global__ void __launch_bounds__(128)
+    elim_gather_fixed_vec_kernel(DevElimPlan p, Mats<double> mats, const int32_t* __restrict__ list, int64_t count) {
+  using T = double;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slot = gid / LANES;
+  const int sub = (int)(gid % LANES);
+  const bool live = slot < count;
+  const int64_t d = live ? list[slot] : 0;
+  T* data = mats.at(blockIdx.z);
+  T acc[NR * NC];
+#pragma unroll
+  for (int e = 0; e < NR * NC; e++) acc[e] = T(0);
+  if (live) {
+    const int tEnd = p.dstTaskPtr[d + 1];
+    int t = p.dstTaskPtr[d] + sub;
+    uint32_t oa = 0, ob = 0;
+    if (t < tEnd) oa = p.taskA[t], ob = p.taskB[t];
+    while (t < tEnd) {
+      const T* __restrict__ a = data + oa;
+      const T* __restrict__ b = data + ob;
+      const int tn = t + LANES;
+      if (tn < tEnd) oa = p.taskA[tn], ob = p.taskB[tn];  // next task's offsets in flight with this task's blocks
+      T av[NC * K], bv[NR * K];
+      loadBlockVec<T, NC * K>(av, a);
+      loadBlockVec<T, NR * K>(bv, b);
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int q = 0; q < K; q++) acc[r * NC + c] += bv[r * K + q] * av[c * K + q];
+      t = tn;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1)
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  if (live) {
+    T* dst = data + p.dstOff[d];
+    const int64_t stride = p.dstStride[d];
+#pragma unroll
+    for (int e = 0; e < NR * NC; e++)
+      if (e % LANES == sub) dst[(e / NC) * stride + (e % NC)] -= acc[e];
+  }
+}
+
+// Gather on the fp64 tensor pipe (round 2): one WARP per destination block, one DMMA (mma.sync.m8n8k4.f64) per pair task.
+// The NR x K block B is the A fragment (lane (g, t) holds B[g][t]), the NC x K block A - transposed - the B fragment
+// (lane (g, t) holds A[g][t]); rows / columns beyond the block and k >= K are zero lanes that do not load. So a task costs
+// each lane two 8-byte loads of CONSECUTIVE addresses across the warp (5 + 5 sectors per task instead of the 36
+// one-sector accesses of the per-lane kernel), the products need neither shuffles (the warp-cooperative SIMT variant
+// spent 11 per task) nor 36 accumulator registers per lane (two hold the lane's share of the 8 x 8 tile): ~30 registers,
+// full occupancy, and the loads of UNROLL tasks are in flight together. The sum of a destination runs over its tasks in
+// list order on UNROLL interleaved accumulators that are added in a fixed order at the end: deterministic.
+__device__ __forceinline__ void dmmaAcc(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+template <int NR, int NC, int K, int UNROLL, bool HEAVY>
+__global__ void __launch_bounds__(256)
+    elim_gather_dmma_kernel(DevElimPlan p, Mats<double> mats) {
+  static_assert(NR <= 8 && NC <= 8 && K <= 4, "one m8n8k4 tile per task");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  // light destinations: a warp each; heavy ones (long task lists): the eight warps of a CTA take consecutive slices of
+  // the list and their partial tiles are added in warp order
+  int64_t d;
+  if (HEAVY) {
+    d = p.heavyList[blockIdx.x];
+  } else {
+    const int64_t w = (int64_t)blockIdx.x * 8 + warp;
+    if (w >= p.numLight) return;
+    d = p.lightList[w];
+  }
+  double* data = mats.at(blockIdx.z);
+  const bool onB = g < NR && t < K, onA = g < NC && t < K;
+  const int idx = g * K + t;
+  int tb = p.dstTaskPtr[d], te = p.dstTaskPtr[d + 1];
+  if (HEAVY) {
+    const int chunk = (te - tb + 7) / 8;
+    tb = min(te, tb + warp * chunk), te = min(te, tb + chunk);
+  }
+  double c[UNROLL][2];
+#pragma unroll
+  for (int u = 0; u < UNROLL; u++) c[u][0] = c[u][1] = 0.0;
+  // the offsets of the next UNROLL tasks are fetched while the blocks of the current ones are in flight
+  uint32_t oa[UNROLL], ob[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; u++) {
+    oa[u] = ob[u] = 0;
+    if (tb + u < te) oa[u] = __ldg(p.taskA + tb + u), ob[u] = __ldg(p.taskB + tb + u);
+  }
+  for (; tb < te; tb += UNROLL) {
+    double a[UNROLL], b[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const bool live = tb + u < te;
+      a[u] = onB && live ? data[ob[u] + idx] : 0.0;
+      b[u] = onA && live ? data[oa[u] + idx] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+      if (tb + UNROLL + u < te) oa[u] = __ldg(p.taskA + tb + UNROLL + u), ob[u] = __ldg(p.taskB + tb + UNROLL + u);
+    // a tile of zeros for a task beyond the end: adds nothing (the branch around an mma would only predicate it)
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) dmmaAcc(c[u][0], c[u][1], a[u], b[u]);
+  }
+#pragma unroll
+  for (int u = 1; u < UNROLL; u++) c[0][0] += c[u][0], c[0][1] += c[u][1];
+  if (HEAVY) {
+    __shared__ double red[8][32][2];
+    red[warp][lane][0] = c[0][0], red[warp][lane][1] = c[0][1];
+    __syncthreads();
+    if (warp != 0) return;
+    c[0][0] = red[0][lane][0], c[0][1] = red[0][lane][1];
+#pragma unroll
+    for (int w = 1; w < 8; w++) c[0][0] += red[w][lane][0], c[0][1] += red[w][lane][1];
+  }
+  if (g < NR) {
+    double* dst = data + p.dstOff[d] + (int64_t)g * p.dstStride[d];
+    if (2 * t < NC) dst[2 * t] -= c[0][0];
+    if (2 * t + 1 < NC) dst[2 * t + 1] -= c[0][1];
   }
 }
 
@@ -677,10 +830,12 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // coalesced ld.global into registers, then the stage - was measured slower on both workloads, BAL 1.92 ms and
   // stress 3.4 ms, and was removed: profiles/README.md.)
   const char* modeEnv = getenv("BSPB200_GATHER");  // read at every call: tests and probes compare the variants
-  // default 1 (per-lane gather, staged heavy list). Mode 3 (warp-per-destination, coalesced loads + shuffle exchange) is
-  // kept as a measured negative: BAL 1.71 vs 1.43 ms, stress 3.80 vs 2.31 ms for the whole elimination (7x the
-  // instructions per task); a quad-transposed load variant measured 2.1 ms for the BAL gather and was dropped.
-  const int mode = modeEnv ? atoi(modeEnv) : 1;
+  // default: 6 for fp64 (tensor-pipe gather: BAL 1.43 -> 0.95 ms, stress 2.31 -> 1.82 ms for the whole elimination), 1
+  // otherwise (per-lane gather, staged heavy list). Measured negatives, kept opt-in: 3 (warp per destination, coalesced
+  // loads + shuffle exchange: BAL 1.71, stress 3.80 ms - 7x the instructions per task), 5 (per-lane with 16-byte loads:
+  // BAL 2.14 ms - 188 registers, half the warps in flight: the kernel is bound by loads in flight, not by L1 sectors);
+  // a quad-transposed load variant measured 2.1 ms for the BAL gather and was dropped.
+  const int mode = modeEnv ? atoi(modeEnv) : (std::is_same<T, double>::value ? 6 : 1);
   auto fixedStaged = [&](auto light, auto heavy, auto lightDirect, int lanes, size_t smem) {
     ensureDynSmem((const void*)light, smem);
     ensureDynSmem((const void*)heavy, smem);
@@ -713,6 +868,52 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
       return warpCoop(elim_gather_warp_kernel<T, 6, 6, 3, 2, false>, elim_gather_warp_kernel<T, 6, 6, 3, 2, true>);
     if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
       return warpCoop(elim_gather_warp_kernel<T, 3, 3, 3, 1, false>, elim_gather_warp_kernel<T, 3, 3, 3, 1, true>);
+  }
+  // BSPB200_GATHER=6: the tensor-pipe gather (fp64, uniform shapes that fit one m8n8k4 tile)
+  if constexpr (std::is_same<T, double>::value) {
+    if (mode == 6 && plan.numLight + plan.numHeavy > 0) {
+      auto launch = [&](auto light, auto heavy) {
+        if (plan.numHeavy > 0) {
+          heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), 256, 0, st>>>(plan, data);
+          B200_LAUNCH_CHECK();
+        }
+        if (plan.numLight > 0) {
+          light<<<dim3((unsigned)ceilDiv(plan.numLight, 8), 1, batch), 256, 0, st>>>(plan, data);
+          B200_LAUNCH_CHECK();
+        }
+      };
+      // tasks in flight per warp: four for the heavy lists and for light lists of medium-sized destinations, ONE when the
+      // typical light destination holds a handful of tasks (an unrolled round costs its DMMAs and predicated loads
+      // whether or not the tasks exist). Measured, BAL (18 tasks per light destination on average): gather 0.65 ms
+      // with 1, 0.69 with 2, 0.75 with 3, 0.81 with 4; stress (all destinations long): 1.39 / 1.39 / 1.36 / 1.32 ms.
+      const bool shortLists = plan.numLight > 0 && plan.lightTasks < 32 * plan.numLight;
+      if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
+        if (shortLists) return launch(elim_gather_dmma_kernel<6, 6, 3, 1, false>, elim_gather_dmma_kernel<6, 6, 3, 4, true>);
+        return launch(elim_gather_dmma_kernel<6, 6, 3, 4, false>, elim_gather_dmma_kernel<6, 6, 3, 4, true>);
+      }
+      if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3) {
+        if (shortLists) return launch(elim_gather_dmma_kernel<3, 3, 3, 1, false>, elim_gather_dmma_kernel<3, 3, 3, 4, true>);
+        return launch(elim_gather_dmma_kernel<3, 3, 3, 4, false>, elim_gather_dmma_kernel<3, 3, 3, 4, true>);
+      }
+    }
+  }
+  // BSPB200_GATHER=5: 16-byte operand loads for the light list (fp64, 6x6x3), staged kernel for the heavy list
+  if constexpr (std::is_same<T, double>::value) {
+    if (mode == 5 && plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
+      if (plan.numLight > 0) {
+        elim_gather_fixed_vec_kernel<6, 6, 3, 8><<<dim3(ceilDiv(plan.numLight * 8, 128), 1, batch), 128, 0, st>>>(
+            plan, data, plan.lightList, plan.numLight);
+        B200_LAUNCH_CHECK();
+      }
+      if (plan.numHeavy > 0) {
+        auto heavy = elim_gather_staged_kernel<T, 6, 6, 3, 128>;
+        const size_t smem = stagedSmemBytes<T, 6, 6, 3>();
+        ensureDynSmem((const void*)heavy, smem);
+        heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), kStagedWarps * 32, smem, st>>>(plan, data, plan.heavyList, plan.numHeavy);
+        B200_LAUNCH_CHECK();
+      }
+      return;
+    }
   }
   const bool staged = mode != 0;
   if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
