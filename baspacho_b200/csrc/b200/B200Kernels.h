@@ -122,6 +122,11 @@ bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
              const int64_t* rowMap = nullptr /* it, same ld) update vec[rowMap[r]] -= L21[r,:] x inside the same launch */,
              Operand<T> vec = Operand<T>() /* the whole vector (C is the lump's slice of it) */);
 
+// lanes of the dense solves: v += the lanes' delta vectors (lane order), deltas zeroed
+template <typename T>
+void gatherLaneDeltas(cudaStream_t st, int batch, int64_t n, int nRHS, int64_t ldc, Operand<T> delta, int64_t laneStride,
+                      int nLanes, Operand<T> v);
+
 // out[i * outRowStride + c * outColStride] (+)= alpha * sum_q M[i][q] * X[c * ldx + q]   (M rows x cols, ldm)
 // (tmp row-major rows x nRHS: strides (nRHS, 1); a column-major vector: strides (1, ld))
 template <typename T>

@@ -305,7 +305,7 @@ struct B200SymbolicCtx : SymbolicCtx {
       if (ln.st) cudaStreamDestroy(ln.st);
       if (ln.done) cudaEventDestroy(ln.done);
     }
-    for (auto* v : {&evDone, &evBg, &evMain})
+    for (auto* v : {&evDone, &evBg, &evMain, &evSolve})
       for (cudaEvent_t ev : *v) cudaEventDestroy(ev);
     if (evLevel) cudaEventDestroy(evLevel);
   }
@@ -433,6 +433,96 @@ struct B200SymbolicCtx : SymbolicCtx {
       fragPlanPtr = std::move(p);
     }
     return *fragPlanPtr;
+  }
+
+  // ---- lanes for the dense part of the solves (round 2): the dense lumps are solved level by level of the supernodal
+  // tree, the lumps of a level on different lanes (streams) with an event per lump instead of one launch after the
+  // other on the solver's stream (GRID 120x120: 99 lumps x 2 directions, ~3.3 us of flag hop per 96 columns each).
+  // Backward, a lump only reads the entries of its ancestors and writes its own: no conflict. Forward, the lumps of a
+  // level scatter into the rows of common ancestors: every lane scatters into its OWN zero-initialised delta vector,
+  // and a lump adds the lanes' deltas of its rows (in lane order: deterministic) before it is solved.
+  struct SolvePlan {
+    int64_t denseFrom = -1, numDense = 0;
+    bool eligible = false;
+    vector<int32_t> level, lane;              // per lump
+    vector<vector<int64_t>> byLevel;          // lumps of a level, ascending
+    vector<vector<int32_t>> srcs, tgts;       // per lump: dense lumps that update it / that own its rows below
+  };
+  std::unique_ptr<SolvePlan> solvePlanPtr;
+  const SolvePlan& solvePlan(int64_t denseFrom) {
+    if (!solvePlanPtr || solvePlanPtr->denseFrom != denseFrom) {
+      auto p = std::make_unique<SolvePlan>();
+      const int64_t nL = skel.numLumps();
+      p->denseFrom = denseFrom, p->numDense = nL - denseFrom;
+      p->level.assign(nL, 0), p->lane.assign(nL, 0), p->srcs.resize(nL), p->tgts.resize(nL);
+      int64_t wide = 0;
+      for (int64_t l = denseFrom; l < nL; l++) {
+        wide += skel.lumpSize(l) >= 2 * kInvBlock;
+        for (int64_t ch = skel.chainColPtr[l]; ch < skel.chainColPtr[l + 1]; ch++) {
+          const int64_t t = skel.spanToLump[skel.chainRowSpan[ch]];
+          if (t != l && (p->tgts[l].empty() || p->tgts[l].back() != t)) p->tgts[l].push_back((int32_t)t);
+        }
+        std::sort(p->tgts[l].begin(), p->tgts[l].end());
+        p->tgts[l].erase(std::unique(p->tgts[l].begin(), p->tgts[l].end()), p->tgts[l].end());
+        for (int32_t t : p->tgts[l]) p->srcs[t].push_back((int32_t)l);
+      }
+      int32_t maxLevel = 0;
+      for (int64_t l = denseFrom; l < nL; l++) {
+        int32_t lv = 0;
+        for (int32_t sLump : p->srcs[l]) lv = std::max(lv, p->level[sLump] + 1);
+        p->level[l] = lv, maxLevel = std::max(maxLevel, lv);
+      }
+      p->byLevel.resize(maxLevel + 1);
+      for (int64_t l = denseFrom; l < nL; l++) {
+        p->lane[l] = (int32_t)(p->byLevel[p->level[l]].size() % std::max(1, numLanes));
+        p->byLevel[p->level[l]].push_back(l);
+      }
+      // worth it when launches of chained solves dominate: several wide lumps, not thousands of tiny ones
+      static const bool on = !getenv("BSPB200_SOLVE_LANES") || atoi(getenv("BSPB200_SOLVE_LANES")) != 0;
+      p->eligible = on && numLanes > 1 && wide >= 4 && p->numDense <= 4096 && (int64_t)p->byLevel.size() < p->numDense;
+      solvePlanPtr = std::move(p);
+    }
+    return *solvePlanPtr;
+  }
+  std::vector<ChainSync> laneChain;
+  std::vector<DevBuf<unsigned>> laneChainBuf;
+  int laneChainBatch = 0;
+  ChainSync* chainSyncLane(int k, int batch) {
+    if (!useChainSolve) return nullptr;
+    const InvPlan& ip = invPlan();
+    if (ip.maxBlocks == 0) return nullptr;
+    if (batch > laneChainBatch || (int)laneChain.size() < numLanes) {
+      B200_CUDA(cudaDeviceSynchronize());
+      laneChain.assign(numLanes, ChainSync());
+      laneChainBuf.clear();
+      laneChainBuf.resize(numLanes);
+      for (int q = 0; q < numLanes; q++) {
+        laneChainBuf[q].resize((size_t)ip.maxBlocks * batch + 1);
+        B200_CUDA(cudaMemset(laneChainBuf[q].ptr(), 0, laneChainBuf[q].size() * sizeof(unsigned)));
+        laneChain[q].flags = laneChainBuf[q].ptr() + 1, laneChain[q].ticket = laneChainBuf[q].ptr();
+        laneChain[q].flagsPerItem = (int)ip.maxBlocks, laneChain[q].ticketBase = 0;
+      }
+      laneChainBatch = batch;
+    }
+    return &laneChain[k];
+  }
+  std::vector<cudaEvent_t> evSolve;
+  DevBuf<unsigned char> solveLaneBuf;  // per lane: the delta vector and the staging of the per-step solves
+  void* solveLaneScratch(size_t bytes) {
+    if (solveLaneBuf.size() < bytes) {
+      B200_CUDA(cudaDeviceSynchronize());
+      solveLaneBuf.resize(bytes);
+      B200_CUDA(cudaMemset(solveLaneBuf.ptr(), 0, bytes));  // the deltas are zero between solves
+    }
+    return solveLaneBuf.ptr();
+  }
+  void ensureSolveLanes(int64_t numDense) {
+    ensureLanes(1, 0);
+    while ((int64_t)evSolve.size() < numDense) {
+      cudaEvent_t ev;
+      B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      evSolve.push_back(ev);
+    }
   }
 
   ChainSync chain;
@@ -876,6 +966,7 @@ struct B200SolveCtx : SolveCtx<TT> {
     }
     denseFrom = std::max(denseFrom, startLump);
     if (denseFrom < upToLump) invertAll(data);
+    if (lanesUsable(denseFrom, startLump, upToLump)) return lanedSolveL(data, denseFrom, C, ldc);
     for (int64_t l = denseFrom; l < upToLump; l++) {
       const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
       const int64_t off = skel.lumpDataOffset(l);
@@ -902,7 +993,9 @@ struct B200SolveCtx : SolveCtx<TT> {
     for (const B200SymElimCtx* e : sym.elimRegistry) denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
     denseFrom = std::max(denseFrom, startLump);
     if (denseFrom < upToLump) invertAll(data);
-    for (int64_t l = upToLump - 1; l >= denseFrom; l--) {
+    const bool laned = lanesUsable(denseFrom, startLump, upToLump);
+    if (laned) lanedSolveLt(data, denseFrom, C, ldc);
+    for (int64_t l = upToLump - 1; l >= denseFrom && !laned; l--) {
       const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
       const int64_t off = skel.lumpDataOffset(l);
       if (rows > 0) {
@@ -923,6 +1016,97 @@ struct B200SolveCtx : SolveCtx<TT> {
     }
   }
   Work<T> temp2() { return temp(1); }
+
+  // ---- the dense part of a whole-matrix solve on lanes (see B200SymbolicCtx::SolvePlan)
+  bool lanesUsable(int64_t denseFrom, int64_t startLump, int64_t upToLump) {
+    static const bool timeline = getenv("BSPB200_PROFILE_TIMELINE") && atoi(getenv("BSPB200_PROFILE_TIMELINE")) != 0;
+    if (upToLump != skel.numLumps() || startLump > denseFrom || denseFrom >= upToLump) return false;
+    if (profileEnabled() && !timeline) return false;
+    if (!sym.useInverseSolve || !sym.useChainSolve) return false;
+    return sym.solvePlan(denseFrom).eligible;
+  }
+  // lane k: [0] its delta vector, [1] its staging for the per-step solves; ldc x nRHS per batch item each
+  Work<T> laneWork(int k, int which, int64_t ldc) {
+    const int64_t stride = ldc * nRHS;
+    const int nLanes = sym.numLanes;
+    T* base = (T*)sym.solveLaneScratch((size_t)2 * nLanes * stride * batch * sizeof(T));
+    Work<T> w;
+    w.stride = stride;
+    w.base = base + ((size_t)which * nLanes + k) * stride * batch;
+    return w;
+  }
+  void lanedSolveL(const TT* data, int64_t denseFrom, TT* C, int64_t ldc) {
+    const auto& P = sym.solvePlan(denseFrom);
+    sym.ensureSolveLanes(P.numDense);
+    const auto& br = sym.belowRows();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    const int nLanes = sym.numLanes;
+    (void)laneWork(0, 0, ldc);  // allocate (and zero) before anything is queued
+    B200_CUDA(cudaEventRecord(sym.evLevel, sym.stream));
+    for (int k = 0; k < nLanes; k++) B200_CUDA(cudaStreamWaitEvent(sym.lanes[k].st, sym.evLevel, 0));
+    static const bool fuseBelow = !(getenv("BSPB200_CHAIN_FUSE_GEMV") && atoi(getenv("BSPB200_CHAIN_FUSE_GEMV")) == 0);
+    for (const auto& lumps : P.byLevel)
+      for (int64_t l : lumps) {
+        const int k = P.lane[l];
+        cudaStream_t st = sym.lanes[k].st;
+        const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
+        const int64_t off = skel.lumpDataOffset(l);
+        for (int32_t sLump : P.srcs[l])
+          if (P.lane[sLump] != k) B200_CUDA(cudaStreamWaitEvent(st, sym.evSolve[sLump - denseFrom], 0));
+        if (!P.srcs[l].empty())
+          gatherLaneDeltas<T>(st, m.batch, n, nRHS, ldc, opnd(laneWork(0, 0, ldc), start), ldc * nRHS * batch, nLanes,
+                              opnd(v, start));
+        BASPACHO_CHECK_EQ(br.ptr[l + 1] - br.ptr[l], rows);
+        bool ready = false;
+        Operand<T> inv = invScratch(off, n, &ready);
+        Operand<T> delta = opnd(laneWork(k, 0, ldc), 0);
+        const bool belowDone =
+            trsvAny<T>(st, m.batch, n, opnd(m, off), n, opnd(v, start), ldc, nRHS, false, opnd(laneWork(k, 1, ldc), 0), inv,
+                       ready, sym.chainSyncLane(k, m.batch), fuseBelow ? rows : 0, br.target.ptr() + br.ptr[l], delta);
+        if (rows > 0 && !belowDone)
+          gemvRows<T>(st, m.batch, rows, n, T(-1), opnd(m, off + n * n), n, opnd(v, start), ldc, delta, 1, ldc, nRHS, true,
+                      br.target.ptr() + br.ptr[l]);
+        B200_CUDA(cudaEventRecord(sym.evSolve[l - denseFrom], st));
+      }
+    for (int k = 0; k < nLanes; k++) {
+      B200_CUDA(cudaEventRecord(sym.lanes[k].done, sym.lanes[k].st));
+      B200_CUDA(cudaStreamWaitEvent(sym.stream, sym.lanes[k].done, 0));
+    }
+  }
+  void lanedSolveLt(const TT* data, int64_t denseFrom, TT* C, int64_t ldc) {
+    const auto& P = sym.solvePlan(denseFrom);
+    sym.ensureSolveLanes(P.numDense);
+    const auto& br = sym.belowRows();
+    Mats<T> m = mats.get(data, sym.stream), v = vecs.get(C, sym.stream);
+    const int nLanes = sym.numLanes;
+    (void)laneWork(0, 0, ldc);
+    B200_CUDA(cudaEventRecord(sym.evLevel, sym.stream));
+    for (int k = 0; k < nLanes; k++) B200_CUDA(cudaStreamWaitEvent(sym.lanes[k].st, sym.evLevel, 0));
+    for (int64_t lv = (int64_t)P.byLevel.size() - 1; lv >= 0; lv--)
+      for (int64_t l : P.byLevel[lv]) {
+        const int k = P.lane[l];
+        cudaStream_t st = sym.lanes[k].st;
+        const int64_t n = skel.lumpSize(l), start = skel.lumpStart[l], rows = skel.lumpTotalRows(l) - n;
+        const int64_t off = skel.lumpDataOffset(l);
+        for (int32_t t : P.tgts[l])
+          if (P.lane[t] != k) B200_CUDA(cudaStreamWaitEvent(st, sym.evSolve[t - denseFrom], 0));
+        Work<T> stage = laneWork(k, 1, ldc);
+        if (rows > 0) {
+          BASPACHO_CHECK_EQ(br.ptr[l + 1] - br.ptr[l], rows);
+          gemvColsT<T>(st, m.batch, rows, n, T(-1), opnd(m, off + n * n), n, opnd(v, 0), 1, ldc, opnd(v, start), ldc, nRHS,
+                       opnd(stage, 0), stage.stride, br.target.ptr() + br.ptr[l]);
+        }
+        bool ready = false;
+        Operand<T> inv = invScratch(off, n, &ready);
+        trsvAny<T>(st, m.batch, n, opnd(m, off), n, opnd(v, start), ldc, nRHS, true, opnd(stage, 0), inv, ready,
+                   sym.chainSyncLane(k, m.batch));
+        B200_CUDA(cudaEventRecord(sym.evSolve[l - denseFrom], st));
+      }
+    for (int k = 0; k < nLanes; k++) {
+      B200_CUDA(cudaEventRecord(sym.lanes[k].done, sym.lanes[k].st));
+      B200_CUDA(cudaStreamWaitEvent(sym.stream, sym.lanes[k].done, 0));
+    }
+  }
 
   // ---- fragmented whole-range ops (reference MatOps.h:168-183, MatOpsFast.cpp:613-1018): level-scheduled block
   // kernels when every lump is a single small span and nRHS == 1 (SparseKernels.cu)

@@ -204,7 +204,12 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* invOut, in
       const double2 v = *reinterpret_cast<const double2*>(D + r * LDQ + c);
       a[r][c] = v.x, a[r][c + 1] = v.y;
     }
-  double rs[8];
+  // The inverse of the factor for the panel solves (X = M L^-T on the tensor pipe) is built alongside: lane j < 8 owns
+  // column j (the other lanes repeat the work of lane j & 7); its entry c only needs row c of the factor, which is
+  // final as soon as column c has been scaled - so the substitution runs in the shadow of the next pivot's rsqrt chain
+  // instead of after the last one. Rows >= e count as identity rows.
+  const int j = lane & 7;
+  double rs[8], w[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     if (c < e) {
@@ -212,34 +217,23 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* invOut, in
 #pragma unroll
       for (int r = c; r < 8; r++) a[r][c] *= rs[c];
 #pragma unroll
-      for (int j = c + 1; j < 8; j++)
+      for (int jj = c + 1; jj < 8; jj++)
 #pragma unroll
-        for (int r = j; r < 8; r++) a[r][j] -= a[r][c] * a[j][c];
+        for (int r = jj; r < 8; r++) a[r][jj] -= a[r][c] * a[jj][c];
+      double v = (c == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < c; q++) v -= a[c][q] * w[q];
+      w[c] = v * rs[c];
     } else {  // identity column
       rs[c] = 1.0;
 #pragma unroll
       for (int r = c; r < 8; r++) a[r][c] = (r == c) ? 1.0 : 0.0;
+      w[c] = (c == j) ? 1.0 : 0.0;
     }
   }
-  // inverse of the factor for the panel solves (X = M L^-T on the tensor pipe): lane j < 8 builds column j by forward
-  // substitution (the other lanes repeat the work of lane j & 7). Rows >= e count as identity rows here.
-  {
-    const int j = lane & 7;
-    double w[8];
+  if (lane < 8) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      double v = (i == j) ? 1.0 : 0.0;
-      if (i < e) {
-#pragma unroll
-        for (int q = 0; q < i; q++) v -= a[i][q] * w[q];
-        v *= rs[i];
-      }
-      w[i] = v;
-    }
-    if (lane < 8) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) invOut[i * 8 + j] = w[i];
-    }
+    for (int i = 0; i < 8; i++) invOut[i * 8 + j] = w[i];
   }
   // lane 0 writes the tile back (one predicate for straight-line vector stores: a store per lane-and-entry predicate
   // compiled into a divergent jump table, 10 k cycles). The entry right of the diagonal of an even row rides along.

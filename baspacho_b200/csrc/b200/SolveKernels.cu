@@ -1033,6 +1033,32 @@ bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   return false;
 }
 
+
+// v[i + rhs * ldc] += sum over the lanes (in lane order) of delta_lane[i + rhs * ldc]; the deltas are zeroed for the next
+// solve. `delta` points at lane 0's entry of row 0 of the lump; laneStride = distance between the lanes' vectors.
+template <typename T>
+__global__ void __launch_bounds__(128) gather_lane_deltas_kernel(int64_t n, int nRHS, int64_t ldc, Operand<T> delta,
+                                                                 int64_t laneStride, int nLanes, Operand<T> v) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * nRHS) return;
+  const int64_t idx = e % n + (e / n) * ldc;
+  T* d = delta.at(blockIdx.z) + idx;
+  T sum = 0;
+  for (int k = 0; k < nLanes; k++) {
+    sum += d[(int64_t)k * laneStride];
+    d[(int64_t)k * laneStride] = T(0);
+  }
+  v.at(blockIdx.z)[idx] += sum;
+}
+template <typename T>
+void gatherLaneDeltas(cudaStream_t st, int batch, int64_t n, int nRHS, int64_t ldc, Operand<T> delta, int64_t laneStride,
+                      int nLanes, Operand<T> v) {
+  if (n <= 0) return;
+  gather_lane_deltas_kernel<T><<<dim3((unsigned)ceilDiv(n * nRHS, 128), 1, batch), 128, 0, st>>>(n, nRHS, ldc, delta, laneStride,
+                                                                                                  nLanes, v);
+  B200_LAUNCH_CHECK();
+}
+
 #define B200_INSTANTIATE_SOLVE(T)                                                                                       \
   template void gemvRows<T>(cudaStream_t, int, int64_t, int64_t, T, Operand<T>, int64_t, Operand<T>, int64_t,          \
                             Operand<T>, int64_t, int64_t, int, bool, const int64_t*);                                   \
@@ -1041,7 +1067,8 @@ bool trsvAny(cudaStream_t st, int batch, int64_t n, Operand<T> L, int64_t ldl, O
   template void symmLower<T>(cudaStream_t, int, int64_t, T, Operand<T>, Operand<T>, int64_t, Operand<T>, int64_t, int); \
   template bool trsvAny<T>(cudaStream_t, int, int64_t, Operand<T>, int64_t, Operand<T>, int64_t, int, bool, Operand<T>, \
                            Operand<T>, bool, ChainSync*, int64_t, const int64_t*, Operand<T>);                          \
-  template void invertBlockList<T>(cudaStream_t, int, const InvBlockDesc*, int64_t, Operand<T>, Operand<T>);
+  template void invertBlockList<T>(cudaStream_t, int, const InvBlockDesc*, int64_t, Operand<T>, Operand<T>);      \
+  template void gatherLaneDeltas<T>(cudaStream_t, int, int64_t, int, int64_t, Operand<T>, int64_t, int, Operand<T>);
 B200_INSTANTIATE_SOLVE(double)
 B200_INSTANTIATE_SOLVE(float)
 

@@ -305,21 +305,19 @@ __device__ __forceinline__ void dmmaAcc(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 template <int NR, int NC, int K, int UNROLL, bool HEAVY>
-__global__ void __launch_bounds__(256)
-    elim_gather_dmma_kernel(DevElimPlan p, Mats<double> mats) {
+__device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double* data, int64_t block) {
   static_assert(NR <= 8 && NC <= 8 && K <= 4, "one m8n8k4 tile per task");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   // light destinations: a warp each; heavy ones (long task lists): the eight warps of a CTA take consecutive slices of
   // the list and their partial tiles are added in warp order
   int64_t d;
   if (HEAVY) {
-    d = p.heavyList[blockIdx.x];
+    d = p.heavyList[block];
   } else {
-    const int64_t w = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t w = block * 8 + warp;
     if (w >= p.numLight) return;
     d = p.lightList[w];
   }
-  double* data = mats.at(blockIdx.z);
   const bool onB = g < NR && t < K, onA = g < NC && t < K;
   const int idx = g * K + t;
   int tb = p.dstTaskPtr[d], te = p.dstTaskPtr[d + 1];
@@ -368,6 +366,21 @@ __global__ void __launch_bounds__(256)
     if (2 * t < NC) dst[2 * t] -= c[0][0];
     if (2 * t + 1 < NC) dst[2 * t + 1] -= c[0][1];
   }
+}
+// one launch: the first numHeavy CTAs take a heavy destination each (they are the long ones: first), the rest eight light
+// destinations each - the two parts share the SMs (stress workload: 1.21 ms against 1.34 for two launches)
+template <int NR, int NC, int K, int ULIGHT, int UHEAVY>
+__global__ void __launch_bounds__(256) elim_gather_dmma_kernel(DevElimPlan p, Mats<double> mats) {
+  double* data = mats.at(blockIdx.z);
+  if ((int64_t)blockIdx.x < p.numHeavy) elimGatherDmmaBody<NR, NC, K, UHEAVY, true>(p, data, blockIdx.x);
+  else elimGatherDmmaBody<NR, NC, K, ULIGHT, false>(p, data, (int64_t)blockIdx.x - p.numHeavy);
+}
+// one part per launch: with short light lists (one task in flight per warp) the light part alone needs 32 registers and
+// runs with twice the warps of the merged kernel - it is bound by loads in flight (BAL: 0.65 ms for both launches
+// against 0.90 merged)
+template <int NR, int NC, int K, int UNROLL, bool HEAVY>
+__global__ void __launch_bounds__(256) elim_gather_dmma_part_kernel(DevElimPlan p, Mats<double> mats) {
+  elimGatherDmmaBody<NR, NC, K, UNROLL, HEAVY>(p, mats.at(blockIdx.z), blockIdx.x);
 }
 
 // Warp-cooperative variant of the fixed-shape gather (round 2). One WARP owns a destination (or, for the heavy ones, a
@@ -716,7 +729,9 @@ __global__ void __launch_bounds__(256) elim_gather_solveL_kernel(DevSkel sk, Dev
 }
 
 // (3) backward: thread per (lump, rhs): x_l -= sum_chains L(row, l)^T v[row]  (each lump owns its output)
-template <typename T>
+// FUSE_DIAG (every lump at most MAXW wide): the transposed solve with the lump's own diagonal block follows in registers
+// (the same operations in the same order as elim_diag_solve_kernel, one launch and one round trip of x less)
+template <typename T, bool FUSE_DIAG>
 __global__ void __launch_bounds__(128) elim_gather_solveLt_kernel(DevSkel sk, Mats<T> mats, Mats<T> vecs, int64_t ldc,
                                                                   int nRHS, int64_t lumpsBegin, int64_t lumpsEnd) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -746,6 +761,18 @@ __global__ void __launch_bounds__(128) elim_gather_solveLt_kernel(DevSkel sk, Ma
         for (int q = 0; q < MAXW; q++)
           if (q < s) acc[q] -= blk[r * s + q] * v;
       }
+    }
+    if (FUSE_DIAG) {
+      const T* __restrict__ L = data + sk.chainData[sk.chainColPtr[lump]];
+#pragma unroll
+      for (int i = MAXW - 1; i >= 0; i--)
+        if (i < s) {
+          T v = acc[i];
+#pragma unroll
+          for (int q = i + 1; q < MAXW; q++)
+            if (q < s) v -= L[q * s + i] * acc[q];
+          acc[i] = v / L[i * s + i];
+        }
     }
 #pragma unroll
     for (int q = 0; q < MAXW; q++)
@@ -872,7 +899,16 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
   // BSPB200_GATHER=6: the tensor-pipe gather (fp64, uniform shapes that fit one m8n8k4 tile)
   if constexpr (std::is_same<T, double>::value) {
     if (mode == 6 && plan.numLight + plan.numHeavy > 0) {
-      auto launch = [&](auto light, auto heavy) {
+      auto launch = [&](auto kernel) {
+        kernel<<<dim3((unsigned)(plan.numHeavy + ceilDiv(plan.numLight, 8)), 1, batch), 256, 0, st>>>(plan, data);
+        B200_LAUNCH_CHECK();
+      };
+      // tasks in flight per warp: four for the heavy lists and for light lists of medium-sized destinations, ONE when the
+      // typical light destination holds a handful of tasks (an unrolled round costs its DMMAs and predicated loads
+      // whether or not the tasks exist). Measured, BAL (18 tasks per light destination on average): gather 0.65 ms
+      // with 1, 0.69 with 2, 0.75 with 3, 0.81 with 4; stress (all destinations long): 1.39 / 1.39 / 1.36 / 1.32 ms.
+      const bool shortLists = plan.numLight > 0 && plan.lightTasks < 32 * plan.numLight;
+      auto launchParts = [&](auto light, auto heavy) {
         if (plan.numHeavy > 0) {
           heavy<<<dim3((unsigned)plan.numHeavy, 1, batch), 256, 0, st>>>(plan, data);
           B200_LAUNCH_CHECK();
@@ -882,19 +918,12 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
           B200_LAUNCH_CHECK();
         }
       };
-      // tasks in flight per warp: four for the heavy lists and for light lists of medium-sized destinations, ONE when the
-      // typical light destination holds a handful of tasks (an unrolled round costs its DMMAs and predicated loads
-      // whether or not the tasks exist). Measured, BAL (18 tasks per light destination on average): gather 0.65 ms
-      // with 1, 0.69 with 2, 0.75 with 3, 0.81 with 4; stress (all destinations long): 1.39 / 1.39 / 1.36 / 1.32 ms.
-      const bool shortLists = plan.numLight > 0 && plan.lightTasks < 32 * plan.numLight;
-      if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3) {
-        if (shortLists) return launch(elim_gather_dmma_kernel<6, 6, 3, 1, false>, elim_gather_dmma_kernel<6, 6, 3, 4, true>);
-        return launch(elim_gather_dmma_kernel<6, 6, 3, 4, false>, elim_gather_dmma_kernel<6, 6, 3, 4, true>);
-      }
-      if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3) {
-        if (shortLists) return launch(elim_gather_dmma_kernel<3, 3, 3, 1, false>, elim_gather_dmma_kernel<3, 3, 3, 4, true>);
-        return launch(elim_gather_dmma_kernel<3, 3, 3, 4, false>, elim_gather_dmma_kernel<3, 3, 3, 4, true>);
-      }
+      if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3)
+        return shortLists ? launchParts(elim_gather_dmma_part_kernel<6, 6, 3, 1, false>, elim_gather_dmma_part_kernel<6, 6, 3, 4, true>)
+                          : launch(elim_gather_dmma_kernel<6, 6, 3, 4, 4>);
+      if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
+        return shortLists ? launchParts(elim_gather_dmma_part_kernel<3, 3, 3, 1, false>, elim_gather_dmma_part_kernel<3, 3, 3, 4, true>)
+                          : launch(elim_gather_dmma_kernel<3, 3, 3, 4, 4>);
     }
   }
   // BSPB200_GATHER=5: 16-byte operand loads for the light list (fp64, 6x6x3), staged kernel for the heavy list
@@ -993,8 +1022,14 @@ void elimSolveLt(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPla
   ProfScope prof(st, KC_SOLVE_ELIM, 0, plan.factorEntries * sizeof(T) * batch);
   // (a warp-per-lump variant with coalesced row reads and the diagonal solve fused in measured slower on the BAL-shaped
   // problem - 0.52 vs 0.46 ms for both directions - and was removed)
-  elim_gather_solveLt_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS,
-                                                                                 plan.lumpsBegin, plan.lumpsEnd);
+  if (plan.uniformLumpSize >= 1 && plan.uniformLumpSize <= 12) {  // MAXW of the kernel: diagonal solve fused
+    elim_gather_solveLt_kernel<T, true><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS,
+                                                                                         plan.lumpsBegin, plan.lumpsEnd);
+    B200_LAUNCH_CHECK();
+    return;
+  }
+  elim_gather_solveLt_kernel<T, false><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS,
+                                                                                        plan.lumpsBegin, plan.lumpsEnd);
   B200_LAUNCH_CHECK();
   elim_diag_solve_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, C, ldc, nRHS, plan.lumpsBegin,
                                                                              plan.lumpsEnd, true);
