@@ -230,6 +230,7 @@ struct B200SymbolicCtx : SymbolicCtx {
     std::vector<int32_t> evIndex;                        // per lump: index of its events, -1 for the small ones
     std::vector<char> hasBg;                             // per lump: receives background contributions
     int64_t numWide = 0;
+    int64_t maxTempElems = 1;                            // largest GEMM temp of a contribution into a wide lump
   };
   std::unique_ptr<EagerPlan> eager;
   std::vector<cudaEvent_t> evDone, evBg, evMain;
@@ -264,6 +265,14 @@ struct B200SymbolicCtx : SymbolicCtx {
             if (src < firstLump) continue;
             e->fromLevel[e->level[src]].push_back(EagerUpdate{t, r});
             if (e->level[src] + 1 < (int32_t)lv) e->hasBg[t] = 1;
+            {
+              const int64_t ord = skel.boardColOrd[r], cb = skel.chainColPtr[src], bb = skel.boardColPtr[src];
+              const int64_t ch0 = skel.boardChainColOrd[bb + ord], ch1 = skel.boardChainColOrd[bb + ord + 1];
+              const int64_t chEnd = skel.boardChainColOrd[skel.boardColPtr[src + 1] - 1];
+              const int64_t rowBegin = skel.chainRowsTillEnd[cb + ch0 - 1];
+              e->maxTempElems = std::max(e->maxTempElems, (skel.chainRowsTillEnd[cb + ch1 - 1] - rowBegin) *
+                                                              (skel.chainRowsTillEnd[cb + chEnd - 1] - rowBegin));
+            }
           }
       eager = std::move(e);
     }
@@ -293,6 +302,14 @@ struct B200SymbolicCtx : SymbolicCtx {
       for (Lane& ln : bgLanes) B200_CUDA(cudaStreamSynchronize(ln.st));
       bgScratch.resize(tempBytesPerLane * bgLanes.size());
     }
+  }
+  // lanes + background lanes each hold one GEMM temp: worth at most a quarter of the free memory
+  bool eagerFits(size_t tempBytesPerLane) {
+    if (!bgLanes.empty() && bgScratch.size() >= tempBytesPerLane * bgLanes.size()) return true;
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) return false;
+    const int nb = getenv("BSPB200_BG_LANES") ? std::max(1, std::min(16, atoi(getenv("BSPB200_BG_LANES")))) : numBgLanes;
+    return tempBytesPerLane * (size_t)(numLanes + nb) < freeB / 4;
   }
   DevBuf<unsigned char> bgScratch;
 
@@ -687,7 +704,8 @@ struct B200NumericCtx : NumericCtx<TT> {
       {
         static const bool timeline = getenv("BSPB200_PROFILE_TIMELINE") && atoi(getenv("BSPB200_PROFILE_TIMELINE")) != 0;
         static const bool eagerOn = !getenv("BSPB200_EAGER") || atoi(getenv("BSPB200_EAGER")) != 0;
-        if (eagerOn && sym.numLanes > 1 && wv.host.numBig >= 2 && (!profileEnabled() || timeline)) {
+        if (eagerOn && sym.numLanes > 1 && wv.host.numBig >= 2 && (!profileEnabled() || timeline) &&
+            sym.eagerFits(eagerTempBytes(sym.eagerPlan(firstSrc, wv.host)))) {
           fusedFactorEager(m, all, wv, firstSrc);
           return;
         }
@@ -740,19 +758,24 @@ struct B200NumericCtx : NumericCtx<TT> {
   }
 
   // the eager schedule (see B200SymbolicCtx::EagerPlan)
+  // a lane's temp in the eager schedule: the largest contribution into a WIDE lump (the solver's own temp also covers the
+  // elimination and the small lumps, and can be much larger)
+  size_t eagerTempBytes(const typename B200SymbolicCtx::EagerPlan& E) const {
+    return (size_t)std::min<int64_t>(E.maxTempElems, std::max<int64_t>(1, tempSize)) * batch * sizeof(T);
+  }
   void fusedFactorEager(const Mats<T>& m, Operand<T> all, const typename B200SymbolicCtx::DevWave& wv, int64_t firstSrc) {
     const auto& E = sym.eagerPlan(firstSrc, wv.host);
     const size_t nLevels = wv.host.levels.size();
     sym.ensureLanes(m.batch, laneTempBytes());
-    sym.ensureEager(E, nLevels, laneTempBytes());
+    sym.ensureEager(E, nLevels, eagerTempBytes(E));
     const int nNear = (int)sym.lanes.size(), nBg = (int)sym.bgLanes.size();
     auto ctxOf = [&](int q) {  // q < nNear: lane, else background lane
       if (q < nNear) return laneCtx(q);
       LaneCtx lc;
       const int b = q - nNear;
       lc.st = sym.bgLanes[b].st;
-      lc.temp.base = (T*)(sym.bgScratch.ptr() + (size_t)b * laneTempBytes());
-      lc.temp.stride = tempSize;
+      lc.temp.base = (T*)(sym.bgScratch.ptr() + (size_t)b * eagerTempBytes(E));
+      lc.temp.stride = (int64_t)(eagerTempBytes(E) / sizeof(T) / batch);
       lc.spanToChainOffset = sym.bgLanes[b].spanToChainOffset.ptr();
       return lc;
     };

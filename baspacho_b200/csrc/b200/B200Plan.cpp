@@ -15,6 +15,18 @@ ElimPlan buildElimPlan(const CoalescedBlockMatrixSkel& sk, int64_t lumpsBegin, i
   if (sk.dataSize() >= (int64_t(1) << 32))
     throw std::runtime_error("B200 sparse elimination plan: factor data beyond 2^32 entries is not supported yet");
 
+  // the plan stores block dimensions in 16 bits and vector / stride positions in 32: refuse what does not fit
+  // instead of truncating (the reference has no such limit; nothing near it occurs in its problem families)
+  if (sk.order() >= (int64_t(1) << 31))
+    throw std::runtime_error("B200 sparse elimination plan: vector order beyond 2^31 is not supported");
+  for (int64_t l = lumpsBegin; l < lumpsEnd; l++)
+    if (sk.lumpSize(l) > 32767) throw std::runtime_error("B200 sparse elimination plan: eliminated lump wider than 32767");
+  for (int64_t sp = p.spanRowBegin; sp < sk.numSpans(); sp++)
+    if (sk.spanStart[sp + 1] - sk.spanStart[sp] > 32767)
+      throw std::runtime_error("B200 sparse elimination plan: row span larger than 32767");
+  for (int64_t l = lumpsEnd; l < sk.numLumps(); l++)
+    if (sk.lumpSize(l) >= (int64_t(1) << 31)) throw std::runtime_error("B200 sparse elimination plan: target lump too wide");
+
   p.uniformLumpSize = lumpsEnd > lumpsBegin ? (int)sk.lumpSize(lumpsBegin) : 0;
   for (int64_t l = lumpsBegin; l < lumpsEnd; l++) {
     if (sk.lumpSize(l) != p.uniformLumpSize) p.uniformLumpSize = 0;

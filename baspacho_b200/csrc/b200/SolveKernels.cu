@@ -905,7 +905,8 @@ __global__ void __launch_bounds__(kChThreads, 1)
         if (lane < kChRows && row < ib) C[(int64_t)(g0 + q) * ldc + i0 + row] = xo;
       }
     }
-    __threadfence();
+    // no fence.sc before the barrier: the barrier orders the CTA's stores before thread 0's release store, which is
+    // cumulative at gpu scope (the explicit fence cost a second memory barrier on every hop of the chain)
     __syncthreads();  // (also: ys / part are reused by the next group of right-hand sides)
     if (tid == 0) stReleaseU32(flg + i, epoch);
   }
