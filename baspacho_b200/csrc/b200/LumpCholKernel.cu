@@ -880,9 +880,15 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
         for (int j = 0; j < 6; j++) {
           const int r = rbase + 8 * i + g, cc = cbase + 8 * j + 2 * t;
           const bool on = rowA0 + r < p.rows && cc < ncOwn && (job.diag != 2 || 6 * wn + j <= 3 * wm + i);
-          if (on)
-            __stcg(reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)ownCol * TB + cc),
-                   make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]));
+          if (on) {
+            double* dst = A + ((int64_t)rowA0 + r) * ld + (int64_t)ownCol * TB + cc;
+            if (job.diag == 2 && 6 * wn + j == 3 * wm + i) {  // a diagonal 8 x 8 tile: entries with column <= row only
+              if (cc <= r) __stcg(dst, av[i][j].x - acc[i][j][0]);
+              if (cc + 1 <= r) __stcg(dst + 1, av[i][j].y - acc[i][j][1]);
+            } else {
+              __stcg(reinterpret_cast<double2*>(dst), make_double2(av[i][j].x - acc[i][j][0], av[i][j].y - acc[i][j][1]));
+            }
+          }
         }
       __syncthreads();
       if (tid == 0) stRelease(segFlag, p.epoch * 256u + (unsigned)job.seg + 1u);

@@ -319,3 +319,104 @@ def test_fp32_gemm_runs_on_tensor_cores_with_fp32_class_accuracy():
             err = torch.tril(err)
             assert torch.equal(torch.triu(c, 1), torch.triu(c0, 1))  # entries above the diagonal are not touched
         assert err.max().item() / scale < 3e-6, (m, n, k, err.max().item() / scale)
+
+
+def _oracle_pair(sizes, ptrs, inds, ranges, **kw):
+    kw = dict(computation_model=_capi.MODEL_B200, **kw)
+    g = bsp.Solver.create(sizes, ptrs, inds, ranges, **kw)
+    o = H.oracle_cpu.OracleSolver.create(sizes, ptrs, inds, ranges, backend=_capi.BACKEND_FAST, num_threads=os.cpu_count(), **kw)
+    return g, o
+
+
+@pytest.mark.parametrize("mode", ["1", "6"])
+@pytest.mark.parametrize("batch", [1, 3])
+def test_elimination_gather_variants_match_oracle_and_are_deterministic(mode, batch, monkeypatch):
+    """The two shipped gathers of the sparse elimination - per-lane SIMT (BSPB200_GATHER=1) and one DMMA per block pair
+    (=6, the fp64 default; reference kernel replaced: MatOpsCuda.cu:235-331, atomics there) - on a bundle-adjustment-
+    shaped problem with long and short task lists, single and batched: each matches the CPU oracle within the stated
+    tolerance and gives the same bits twice (fixed summation order, no atomics)."""
+    import torch
+    monkeypatch.setenv("BSPB200_GATHER", mode)
+    sizes, ptrs, inds = H.ba_problem(6000, 40, seed=11)
+    g, o = _oracle_pair(sizes, ptrs, inds, [0, 6000], find_sparse_elim_ranges=True)
+    mask = H.flat_lower_mask(g)
+    datas = [H.make_data(g, 50 + b, np.float64, 1.3) for b in range(batch)]
+    rhss = [H.oapi().random_data_array(g.order, -1, 1, 70 + b) for b in range(batch)]
+    runs = []
+    for rep in range(2):
+        ds, xs = [torch_of(d) for d in datas], [torch_of(r) for r in rhss]
+        if batch == 1:
+            g.factor(ds[0])
+            g.solve(ds[0], xs[0])
+        else:
+            g.factor_batched(ds)
+            g.solve_batched(ds, xs)
+        torch.cuda.synchronize()
+        runs.append(([d.cpu().numpy() for d in ds], [x.cpu().numpy() for x in xs]))
+    for b in range(batch):
+        assert np.array_equal(runs[0][0][b][mask], runs[1][0][b][mask]) and np.array_equal(runs[0][1][b], runs[1][1][b])
+        ref_f, ref_x = datas[b].copy(), rhss[b].copy()
+        o.factor(ref_f)
+        o.solve(ref_f, ref_x)
+        assert H.ulp_err(runs[0][0][b], ref_f, mask) <= H.FACTOR_ULPS
+        assert H.ulp_err(runs[0][1][b], ref_x) <= H.SOLVE_ULPS
+
+
+def test_eager_schedule_and_solve_lanes_are_deterministic_and_match_oracle():
+    """Supernodal tree with many wide lumps (grid problem, no sparse elimination): the factor runs the eager source-driven
+    schedule (per-lump events, background lanes), the solve the lanes with lane-private delta vectors (DESIGN.md §5;
+    reference loop: Solver.cpp:198-218 / 268-397, strictly sequential there). Three runs must agree bit for bit - the
+    order of the contributions into a lump and of the lanes' deltas is fixed, whatever the streams do - and match the
+    CPU oracle; two right-hand sides exercise the nRHS > 1 path of the delta vectors."""
+    import torch
+    sizes, ptrs, inds = H.oapi().gen_pattern_arrays(H.GEN_GRID, [56, 52, 1.0, 2], 6, 6, 23)
+    g, o = _oracle_pair(sizes, ptrs, inds, (), find_sparse_elim_ranges=False)
+    widths = np.diff(g.lumpStart)
+    assert (widths >= 384).sum() >= 4 and (widths >= 192).sum() >= 4  # tile-DAG lumps, eager schedule, solve lanes eligible
+    data = H.make_data(g, 5, np.float64, 1.2)
+    rhs = H.oapi().random_data_array(g.order * 2, -1, 1, 6).reshape(2, g.order)
+    mask = H.flat_lower_mask(g)
+    outs = []
+    for rep in range(3):
+        d, x = torch_of(data), torch_of(rhs)
+        g.factor(d)
+        g.solve(d, x)
+        torch.cuda.synchronize()
+        outs.append((d.cpu().numpy(), x.cpu().numpy()))
+    for f, x in outs[1:]:
+        assert np.array_equal(f[mask], outs[0][0][mask]) and np.array_equal(x, outs[0][1])
+    ref_f = data.copy()
+    o.factor(ref_f)
+    assert H.ulp_err(outs[0][0], ref_f, mask) <= H.FACTOR_ULPS_LONG_SUMS
+    for k in range(2):
+        ref_x = rhs[k].copy()
+        o.solve(ref_f, ref_x)
+        assert H.ulp_err(outs[0][1][k], ref_x) <= H.SOLVE_ULPS
+
+
+@pytest.mark.parametrize("seg,lag", [("0", "0"), ("3", "0"), ("5", "2")])
+def test_tile_dag_cholesky_job_list_variants(seg, lag, monkeypatch):
+    """lump_chol_kernel with whole sums per job (default) and with the sums cut into segments applied in place
+    (BSPB200_LUMPCHOL_SEG / _LAG: measured slower, kept as a switch): same factor within a few ulps of a dense
+    float64 Cholesky, for a square lump and a trapezoid with a partial last block (replaces cusolverDnDpotrf +
+    cublasDtrsm on a lump column, MatOpsCuda.cu:508-566)."""
+    import torch
+    monkeypatch.setenv("BSPB200_LUMPCHOL_SEG", seg)
+    monkeypatch.setenv("BSPB200_LUMPCHOL_LAG", lag)
+    api = bsp.api()
+    torch.manual_seed(3)
+    for n, rb in ((1346, 0), (1010, 530)):
+        M = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        A11 = M @ M.T + n * torch.eye(n, dtype=torch.float64, device="cuda")
+        A = torch.cat([A11, torch.randn(rb, n, dtype=torch.float64, device="cuda")]).contiguous()
+        W = A.clone()
+        st = torch.cuda.current_stream().cuda_stream
+        api.check(api.dev_potrf(0, n, rb, W.data_ptr(), n, st))
+        torch.cuda.synchronize()
+        Lref = torch.linalg.cholesky(A11)
+        got = torch.tril(W[:n])
+        assert float((got - Lref).abs().max() / Lref.abs().max()) < 64 * H.EPS64
+        assert torch.equal(torch.triu(W[:n], 1), torch.triu(A11, 1))  # entries above the diagonal are not touched
+        if rb:
+            Xref = torch.linalg.solve_triangular(Lref, A[n:].T, upper=False).T
+            assert float((W[n:] - Xref).abs().max() / Xref.abs().max()) < 256 * H.EPS64
