@@ -678,20 +678,18 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 6; j++) {
             const int r = rbase + 8 * i + g, cc = 8 * (2 * j + wn) + 2 * t;
-            *reinterpret_cast<double2*>(Eb + r * LDE + cc) = make_double2(x[i][j][0], x[i][j][1]);
+            const double2 v = make_double2(x[i][j][0], x[i][j][1]);
+            *reinterpret_cast<double2*>(Eb + r * LDE + cc) = v;
+            // L1 -> global straight from the registers (plain stores, nobody waits for them here: the flag is
+            // published after the next product; bulk row copies out of Eb cost a proxy fence + 96 issues + a wait: 3 k cycles)
+            if (rowA0 + r < p.rows) __stcg(reinterpret_cast<double2*>(A + ((int64_t)rowA0 + r) * ld + (int64_t)c * TB + cc), v);
           }
-        fenceProxyAsync();  // L1 goes to global by bulk copies out of Eb
       }
       // a full interior block overwrites its whole lower triangle below (what is left of W_{d-1} above the diagonal of
       // the diagonal tiles is never read); a partial one must be zero outside its valid region
       if (nd < TB || rowA0 + TB > p.rows)
         for (int idx = tid; idx < TB * LDQ / 2; idx += kConsumers) reinterpret_cast<double2*>(S)[idx] = make_double2(0.0, 0.0);
       consumerBar();
-      const bool l1Store = c >= 0 && tid < TB && rowA0 + tid < p.rows;
-      if (l1Store) {  // one row each (768 bytes; the block column c = d - 1 is never the partial last one)
-        bulkStore(A + ((int64_t)rowA0 + tid) * ld + (int64_t)c * TB, smemU32(Eb + tid * LDE), TB * 8);
-        bulkCommit();
-      }
       LC_CSTAMP(5)
       mbarWait(pBar, pUses & 1);  // P has landed
       pUses++;
@@ -747,9 +745,8 @@ __global__ void __launch_bounds__(kThreads, 1) lump_chol_kernel(const __grid_con
             }
           }
       }
-      if (l1Store) bulkWaitAll();  // L(d,d-1) has landed (issued before the products: long done)
       consumerBar();
-      if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);
+      if (c >= 0 && tid == 0) stRelease(p.done + (int64_t)d * p.nbc + c, p.epoch);  // L(d,d-1): stored before the product
       LC_CSTAMP(7)
       potrfTile(S, nd, colbuf, tid, warp, lane, (p.dbg && d == 20) ? p.dbg + 63 * 16 : nullptr);
       LC_CSTAMP(8)
