@@ -29,7 +29,7 @@ DECLARED_SYMBOLS = [
     "last_error", "version", "create_solver", "create_solver_from_skel", "destroy_solver", "solver_query",
     "solver_array", "densify", "damp", "block_offset", "work_estimate", "set_stream", "set_fused", "factor",
     "factor_batched", "solve", "solve_batched", "add_mv_from", "pseudo_factor_from", "do_elimination",
-    "factor_solve_host", "host_copy_bytes", "factor_solve_host_batched", "device_accessor", "dev_gemm_nt", "dev_potrf", "profile_enable", "profile_report", "debug_read", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
+    "factor_solve_host", "host_copy_bytes", "factor_solve_host_batched", "device_accessor", "dev_gemm_nt", "dev_potrf", "lumpchol_job_list", "profile_enable", "profile_report", "debug_read", "launch_count", "gen_pattern", "pattern_order", "pattern_nnz", "pattern_copy",
     "pattern_free", "random_data", "fill_reducing_permutation",
 ]
 
@@ -76,6 +76,7 @@ class CApi:
         if prefix == "bspb200_":
             f("dev_gemm_nt", C.c_int, [C.c_int, c_i64, c_i64, c_i64, C.c_double, vp, c_i64, vp, c_i64, C.c_double, vp, c_i64, C.c_int, vp])
             f("dev_potrf", C.c_int, [C.c_int, c_i64, c_i64, vp, c_i64, vp])
+            f("lumpchol_job_list", c_i64, [C.c_int, C.c_int, C.c_int, C.c_int, vp, c_i64])
             f("device_accessor", C.c_int, [vp, C.POINTER(vp)])
             f("host_copy_bytes", C.c_int, [vp, c_i64p, c_i64p])
             f("factor_solve_host_batched", C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), c_i64, C.c_int])

@@ -1135,6 +1135,20 @@ int64_t lumpCholDebugRead(void* out, int64_t bytes) {
   return n;
 }
 
+// host only (no device needed): the job list lump_chol_kernel would run for a shape, as 5 numbers per job
+// {block row, block column, first K block, end K block, type | last << 4} (type 0 regular tile, 1 = M1, 2 = P of a diagonal
+// block); returns the number of jobs, copies at most `capJobs` of them. For the schedule-validity test.
+int64_t lumpCholJobList(int nbc, int nbr, int seglen, int lag, int32_t* out, int64_t capJobs) {
+  if (seglen <= 0) seglen = 1 << 20;
+  const std::vector<int4> jobs = buildJobs(nbc, nbr, seglen, lag);
+  for (int64_t i = 0; i < (int64_t)jobs.size() && i < capJobs; i++) {
+    const int4 q = jobs[i];
+    out[5 * i + 0] = q.x, out[5 * i + 1] = q.y, out[5 * i + 2] = q.z & 0xfffff, out[5 * i + 3] = q.w & 0xfffffff;
+    out[5 * i + 4] = ((q.w >> 28) & 3) | (((q.w >> 30) & 1) << 4);
+  }
+  return (int64_t)jobs.size();
+}
+
 int lumpCholMinWidth() {
   const char* e = getenv("BSPB200_LUMPCHOL_MIN");
   return e ? atoi(e) : 384;

@@ -252,6 +252,13 @@ int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha
   });
 }
 
+int64_t bspb200_lumpchol_job_list(int block_cols, int block_rows, int segment_len, int lag, int32_t* jobs_out,
+                                  int64_t cap_jobs) {
+  int64_t n = -1;
+  guarded([&] { n = BaSpaCho::b200::lumpCholJobList(block_cols, block_rows, segment_len, lag, jobs_out, cap_jobs); });
+  return n;
+}
+
 int bspb200_dev_potrf(int dtype, int64_t n, int64_t rows_below, void* A, int64_t ld, void* stream) {
   return guarded([&] {
     using namespace BaSpaCho::b200;

@@ -139,6 +139,11 @@ int bspb200_dev_gemm_nt(int dtype, int64_t m, int64_t n, int64_t k, double alpha
 /* in-place Cholesky of the (n + rows_below) x n trapezoid (top n x n = diagonal block, lower triangle), ld >= n */
 int bspb200_dev_potrf(int dtype, int64_t n, int64_t rows_below, void* A, int64_t ld, void* stream);
 
+/* host only: the ticket-ordered job list of the tile-DAG Cholesky kernel for a lump of block_cols x block_rows tiles of 96
+ * (segment_len 0 = whole sums; see LumpCholKernel.cu buildJobs): 5 int32 per job {block row, block column, first K block,
+ * end K block, type | last << 4}; returns the number of jobs (copies at most cap_jobs). No device is touched. */
+int64_t bspb200_lumpchol_job_list(int block_cols, int block_rows, int segment_len, int lag, int32_t* jobs_out, int64_t cap_jobs);
+
 /* per-kernel-class profiling (CUDA events around every launch, algorithmic flops/bytes beside the time); the
  * report is a JSON object {class: {launches, ms, flops, bytes}}; returns its length (copied up to cap-1 + NUL) */
 int bspb200_profile_enable(int on);
