@@ -136,6 +136,17 @@ struct B200SymbolicCtx : SymbolicCtx {
     return e;
   }
 
+  // sub-plans of a registered elimination range (BSPB200_ELIM_CHUNKS), built once
+  std::map<const B200SymElimCtx*, std::vector<std::unique_ptr<B200SymElimCtx>>> elimChunkPlans;
+  const std::vector<std::unique_ptr<B200SymElimCtx>>& elimChunks(const B200SymElimCtx* e, int n) {
+    auto& v = elimChunkPlans[e];
+    if (v.empty()) {
+      const int64_t b = e->dev.lumpsBegin, len = e->dev.lumpsEnd - b;
+      for (int i = 0; i < n; i++) v.push_back(makeElimCtx(b + len * i / n, b + len * (i + 1) / n));
+    }
+    return v;
+  }
+
   NumericCtxBase* createNumericCtxForType(std::type_index tIdx, int64_t tempBufSize, int batchSize) override;
   SolveCtxBase* createSolveCtxForType(std::type_index tIdx, int nRHS, int batchSize) override;
 
@@ -691,6 +702,27 @@ struct B200NumericCtx : NumericCtx<TT> {
       denseFrom = std::max(denseFrom, e->dev.lumpsEnd);
       if (e->dev.lumpsEnd > upToLump) return;
       if (startLump > e->dev.lumpsBegin) continue;
+      // BSPB200_ELIM_CHUNKS=N > 1: the range in N pieces, each factored and gathered before the next, so that a piece's
+      // columns are still in L2 when its pair products read them back (sub-plans as in the host-staged pipeline)
+      // Pays when the destinations have LONG task lists (stress workload, 1 M points on 200 cameras: gather 1.21 -> 0.85
+      // ms with 8 pieces) and costs when they are short, because every piece walks its own list of destinations (BAL,
+      // 26 tasks per destination: 0.71 -> 1.40 / 1.75 / 2.56 ms with 4 / 8 / 16 pieces). Default: pieces of ~64 MB of
+      // eliminated columns when the average list holds 256 tasks or more.
+      static const int envChunks = getenv("BSPB200_ELIM_CHUNKS") ? std::max(1, atoi(getenv("BSPB200_ELIM_CHUNKS"))) : 0;
+      int nChunks = envChunks;
+      if (nChunks == 0) {
+        const double tasks = e->dev.gatherFlops / std::max(1.0, 2.0 * e->dev.uniRows * e->dev.uniCols * e->dev.uniK);
+        const bool longLists = e->dev.uniK > 0 && e->dev.numDst > 0 && tasks >= 256.0 * e->dev.numDst;
+        nChunks = longLists ? (int)std::min(16.0, e->dev.factorEntries * sizeof(T) / (64.0 * 1024 * 1024)) : 1;
+      }
+      if (nChunks > 1 && e->dev.lumpsEnd - e->dev.lumpsBegin >= 64 * nChunks) {
+        for (const auto& ch : sym.elimChunks(e, nChunks)) {
+          elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, ch->dev.lumpsBegin, ch->dev.lumpsEnd, ch->dev.uniformLumpSize,
+                             2.0 * ch->dev.factorEntries * sizeof(T));
+          elimGather<T>(sym.stream, m.batch, ch->dev, m);
+        }
+        continue;
+      }
       elimFactorLumps<T>(sym.stream, m.batch, sym.dsk, m, e->dev.lumpsBegin, e->dev.lumpsEnd, e->dev.uniformLumpSize,
                          2.0 * e->dev.factorEntries * sizeof(T));
       elimGather<T>(sym.stream, m.batch, e->dev, m);
