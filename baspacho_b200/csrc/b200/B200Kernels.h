@@ -68,6 +68,7 @@ void potrfTrapezoid(cudaStream_t st, int batch, int64_t n, int64_t rowsBelow, Op
 bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int64_t ld);
 int lumpCholMinWidth();
 int64_t lumpCholDebugRead(void* out, int64_t bytes);
+void lumpCholSetConcurrency(int n);
 int64_t lumpCholJobList(int nbc, int nbr, int seglen, int lag, int32_t* out, int64_t capJobs);
 
 // diagonal Cholesky + triangular solve of many small lump columns in one launch (work list on the device)

@@ -842,11 +842,13 @@ struct B200NumericCtx : NumericCtx<TT> {
         mainWork = true;
       }
       // the wide lumps of the level: every contribution is already queued on their lane
+      lumpCholSetConcurrency((int)std::min<size_t>(L.bigLumps.size(), (size_t)nNear));
       for (int64_t l : L.bigLumps) {
         LaneCtx lc = laneCtx(E.laneOf[l]);
         factorLumpColumn(m, l, &lc);
         B200_CUDA(cudaEventRecord(sym.evDone[E.evIndex[l]], lc.st));
       }
+      lumpCholSetConcurrency(0);
       // contributions of this level's lumps: next-level targets first (their lanes), then the background
       waited.clear();
       for (int pass = 0; pass < 2; pass++)

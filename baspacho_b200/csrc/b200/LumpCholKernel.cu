@@ -1149,6 +1149,11 @@ int64_t lumpCholJobList(int nbc, int nbr, int seglen, int lag, int32_t* out, int
   return (int64_t)jobs.size();
 }
 
+// hint of the caller's host thread: this many tile-DAG launches are about to run side by side (lumps of one tree level on
+// their lanes); 0 / 1 = alone. The launch then asks for its share of the SMs instead of all it could use alone.
+thread_local int tlsLumpConcurrency = 0;
+void lumpCholSetConcurrency(int n) { tlsLumpConcurrency = n; }
+
 int lumpCholMinWidth() {
   const char* e = getenv("BSPB200_LUMPCHOL_MIN");
   return e ? atoi(e) : 384;
@@ -1232,6 +1237,8 @@ bool lumpCholesky(cudaStream_t st, int64_t n, int64_t rowsBelow, double* A, int6
   // 48: 0.77, 96: 0.77; n = 1000 + 700 rows: 16 CTAs 0.60 ms, 24: 0.44, 32: 0.41, 48: 0.41.
   const double flops = (double)n * n * n / 3 + (double)rowsBelow * n * n;
   int64_t want = (int64_t)(2.0 * flops / (p.nbc * 36.5e-6 * 150e9)) + (int64_t)(0.4 * p.nbc) + 3;
+  // concurrent lumps (GRID 120x120, leaf level on 8 lanes: factor 16.9 ms uncapped, 16.1 ms with 40 CTAs each)
+  if (tlsLumpConcurrency >= 4) want = std::min<int64_t>(want, std::max<int64_t>(24, 2 * (int64_t)sms / tlsLumpConcurrency + 3));
   if (const char* e = getenv("BSPB200_LUMPCHOL_GRID")) want = atoi(e);
   // at least two CTAs: the chain CTA only consumes what the accumulate jobs of the others publish
   const int grid = (int)std::max<int64_t>(2, std::min<int64_t>({(int64_t)sms, jobs + 1, std::max<int64_t>(want, 16)}));

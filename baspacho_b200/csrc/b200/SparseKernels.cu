@@ -321,6 +321,13 @@ __device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double*
   const bool onB = g < NR && t < K, onA = g < NC && t < K;
   const int idx = g * K + t;
   int tb = p.dstTaskPtr[d], te = p.dstTaskPtr[d + 1];
+  // the destination's own entries are requested now, with the first tasks: one round trip less at the end
+  double* dst = data + p.dstOff[d] + (int64_t)g * p.dstStride[d];
+  double old0 = 0.0, old1 = 0.0;
+  if (!HEAVY && g < NR) {
+    if (2 * t < NC) old0 = dst[2 * t];
+    if (2 * t + 1 < NC) old1 = dst[2 * t + 1];
+  }
   if (HEAVY) {
     const int chunk = (te - tb + 7) / 8;
     tb = min(te, tb + warp * chunk), te = min(te, tb + chunk);
@@ -362,9 +369,13 @@ __device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double*
     for (int w = 1; w < 8; w++) c[0][0] += red[w][lane][0], c[0][1] += red[w][lane][1];
   }
   if (g < NR) {
-    double* dst = data + p.dstOff[d] + (int64_t)g * p.dstStride[d];
-    if (2 * t < NC) dst[2 * t] -= c[0][0];
-    if (2 * t + 1 < NC) dst[2 * t + 1] -= c[0][1];
+    if (HEAVY) {
+      if (2 * t < NC) dst[2 * t] -= c[0][0];
+      if (2 * t + 1 < NC) dst[2 * t + 1] -= c[0][1];
+    } else {
+      if (2 * t < NC) dst[2 * t] = old0 - c[0][0];
+      if (2 * t + 1 < NC) dst[2 * t + 1] = old1 - c[0][1];
+    }
   }
 }
 // one launch: the first numHeavy CTAs take a heavy destination each (they are the long ones: first), the rest eight light
@@ -918,6 +929,7 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
           B200_LAUNCH_CHECK();
         }
       };
+      // (two tasks in flight inside 40 registers - 6 CTAs per SM, 96 tasks in flight against 64 - measured 0.79 vs 0.70 ms)
       if (plan.uniRows == 6 && plan.uniCols == 6 && plan.uniK == 3)
         return shortLists ? launchParts(elim_gather_dmma_part_kernel<6, 6, 3, 1, false>, elim_gather_dmma_part_kernel<6, 6, 3, 4, true>)
                           : launch(elim_gather_dmma_kernel<6, 6, 3, 4, 4>);
