@@ -202,6 +202,42 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa_node(local):
+    """One process per GPU: run (and first-touch / pin host buffers) on the CPUs of the NUMA node the GPU hangs off, so
+    that the end-to-end leg's pinned staging buffers and the H2D DMA stay on the GPU's side of the socket interconnect
+    (8 ranks uploading 566 MB each per step otherwise share one socket's memory controllers). Best effort: silently
+    does nothing when sysfs / NVML do not tell, or when the node's CPUs are not in this process's affinity mask."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis else local
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """the reference's CPU path (restated BLAS backend, all host threads) on the same workload; loads oracle/ only"""
     rank, world, _ = dist_setup(args.gpus)
@@ -499,6 +535,8 @@ def run_b200(args):
     import torch
     rank, world, local = dist_setup(args.gpus)
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (no CPU fallback)"
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
+    log(f"rank {rank}: numa pinning {numa}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
