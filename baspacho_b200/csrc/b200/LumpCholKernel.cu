@@ -9,21 +9,22 @@
 //     L(i,c) = ( A(i,c) - sum_{k<c} L(i,k) L(c,k)^T ) W_c^T ,     W_c = L(c,c)^-1 ,
 // the sum running over the already finished tiles of block rows i and c (left-looking: every tile is read-modify-
 // written exactly once, its accumulator lives in registers for the whole sum). Jobs are handed out by an arrival
-// ticket in column-major order, so a job only ever waits for jobs with smaller tickets, which are finished or being
+// ticket in an order in which a job only ever waits for jobs with smaller tickets, which are finished or being
 // executed by resident CTAs: no deadlock whatever the number of co-resident CTAs. A finished tile is published with
-// store -> fence -> release-store of the launch's epoch into its flag; the loader polls the flags of the two tiles
+// store -> barrier -> release-store of the launch's epoch into its flag; the loader polls the flags of the two tiles
 // of a K block with acquire loads before requesting them.
 //
-// The critical path of a blocked Cholesky is the chain of diagonal blocks. Here block d is a special job that owns
-// the pair (d, d-1), (d, d): it accumulates both tiles in one 96 x 192 product while the previous diagonal block is
-// still being factored, and when W_{d-1} is published only   L(d,d-1) = M W^T  ->  D -= L(d,d-1) L(d,d-1)^T  ->
-// potrf(D)  ->  W_d   remain, all inside the CTA (one flag hop per block column instead of kernel boundaries).
-// Everything else - the bulk of the flops - fills the other SMs in the shadow of that chain.
+// The critical path of a blocked Cholesky is the chain of diagonal blocks. Here ONE CTA (the first to arrive) owns that
+// chain: for block d only   L(d,d-1) = M1 W^T  ->  D = P - L(d,d-1) L(d,d-1)^T  ->  potrf(D)  ->  W_d   run there, with
+// W_{d-1} still in its shared memory; the sums M1 = A(d,d-1) - sum, P = A(d,d) - sum are accumulated ahead of it by jobs
+// of the other CTAs and handed over through global memory. Everything else - the bulk of the flops - fills the other
+// SMs in the shadow of that chain.
 //
 // Data path: operand tiles travel HBM/L2 -> shared memory by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, one
 // elected producer thread, full/empty mbarrier ring of 4 stages), the contraction runs on the fp64 tensor pipe
 // (mma.sync.m8n8k4.f64 = DMMA; tcgen05.mma has no f64 kind), accumulators in registers. The diagonal 96 x 96
-// Cholesky is the register-resident right-looking scheme of panel2_kernel (4 columns per step, branch-free rsqrt).
+// Cholesky is blocked over 8-column panels: panel solve and trailing update on DMMA, the 8 x 8 pivot tile factored by one
+// warp with every lane on its own register copy (potrfTile / factorTile8 below).
 //
 // Determinism: the summation order of every entry is fixed (k ascending), independent of the schedule.
 // Non-SPD input: a non-positive pivot yields NaN, which propagates; flags are still published, nothing hangs.
@@ -144,6 +145,8 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double rsqrtNewton(double x) {  // see DenseKernels.cu rsqrtFast
+  // rsqrt.approx.f64 is good to ~20 bits; two Newton steps reach full precision. The dependent chain is MUFU (17.5
+  // cycles) + 6 fp64 operations of 9 cycles (profiles/r02_ubench_fp64_pipe.txt): ~72 cycles per pivot.
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double hx = 0.5 * x;
@@ -247,12 +250,15 @@ __device__ __forceinline__ void factorTile8(double* D, int e, double* invOut, in
 
 // In-place Cholesky of the lower triangle of S ([96][LDQ], zero outside the valid region) by the 256 threads of the CTA,
 // blocked over 8-column panels with a one-panel lookahead:
-//   (b) thread per row: the rows below the diagonal tile are solved against its factor (from `fac`) by substitution;
+//   (b) the rows below the diagonal tile are solved against its factor: X = M L^-T with the tile's 8 x 8 inverse (from
+//       `fac2`, a by-product of factorTile8), one 8 x 8 tile = two DMMA at a time, tiles over the warps;
 //   (c) the trailing update  S22 -= X X^T  runs on the tensor pipe, one 8 x 8 tile (K = 8: two DMMA) at a time: warp 0
-//       updates the NEXT diagonal tile first and factors it right away (factorTile8) while the warps 1..7 work through
-//       the other lower tiles - the serial pivot chain of panel p + 1 hides behind the update of panel p.
-// Two barriers per panel. (The register-resident scheme of panel2_kernel, four columns per step with all 256 threads
-// updating their slots with DFMA, measured 57 k cycles here; this blocked scheme without the lookahead 35 k.)
+//       updates the NEXT diagonal tile first and factors it right away (factorTile8) while the warps 1, 2, 3, 5, 6, 7
+//       work through the other lower tiles - the serial pivot chain of panel p + 1 hides behind the update of panel p.
+// Two barriers per panel; 26 k cycles for the 96 x 96 block. (Measured on the way: the register-resident scheme of
+// panel2_kernel - four columns per step, all 256 threads updating their slots with DFMA - 57 k cycles; this blocked
+// scheme without the lookahead 35 k; with a lane-distributed pivot tile (shuffles on the pivot chain) and row solves by
+// substitution 36.8 k; redundant per-lane pivot tile 31.6 k; DMMA row solves 27.6 k; inverse inside the pivot loop 26.0 k.)
 // nd < 96: columns >= nd act as identity; rows >= nd with entries in columns < nd (rows below a partial last diagonal
 // block) ride along as the extra rows of a trapezoid and come out as M L^-T.
 __device__ __forceinline__ void potrfTile(double* S, int nd, double* fac2 /* [2][72] */, int tid, int warp, int lane,
@@ -440,15 +446,18 @@ __device__ __forceinline__ void invertTile(const double* S, double* Wm, double* 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-// Two job streams. Diagonal job d (d = 0 .. nbc-1) owns the tiles (d, d-1) and (d, d); the first `chainCtas` CTAs to
-// arrive take them in order and do nothing else while there are any: a diagonal job accumulates 2 (d - 1) tile products
-// before it reaches the serial part of the chain, and must have started that long before the chain arrives (handed
-// out in column-major order with the regular tiles, the late diagonal jobs started late and the run ended in a tail of
-// single CTAs accumulating for ~0.9 ms). Regular job t: the remaining tiles in column-major order, rows
-// i = c+2 .. nbr-1 of block column c (i = c+1 too where there is no diagonal block c+1: rows below the lump's square).
-// A job only waits for jobs with smaller tickets of its own stream, or for jobs of the other stream that in turn only
-// depend on smaller tickets: no deadlock whatever the number of co-resident CTAs, as long as chain CTAs are the first to
-// arrive (they are resident by construction).
+// Roles. The first CTA to arrive is the CHAIN CTA: it walks the diagonal blocks d = 0 .. nbc-1 and does the serial part
+// of each (triangular product with the inverse of the previous block, which is still in its shared memory, D = P - L L^T,
+// Cholesky of D, inverse), nothing else while there are any. Every other CTA takes JOBS by an arrival ticket from one
+// list built on the host (buildJobs below): the tiles (i, c) below the sub-diagonal - rows i = c+2 .. nbr-1 of block
+// column c, i = c+1 too where there is no diagonal block c+1 (rows below the lump's square) - and, per diagonal block, the
+// two accumulate jobs whose results (M1 = A(d,d-1) - sum, P = A(d,d) - sum) are handed to the chain through global memory.
+// The list is sorted by the chain step that makes a job runnable, hand-overs first: a job only waits for jobs with
+// smaller tickets and for chain steps that in turn only wait for hand-overs with smaller tickets - no deadlock whatever
+// the number of co-resident CTAs (tests/test_lumpchol_schedule.py replays this argument on the list).
+// History (profiles/README.md): diagonal jobs as one unit on a set of chain CTAs (2.42 ms on the 5226-wide lump: a flag hop
+// and a store / load of the inverse per block column on the chain) -> one chain CTA + dedicated accumulate CTAs (the
+// accumulate jobs became the bound) -> one sorted list for everybody (2.28 ms).
 struct Job {
   int i, c;     // tile (block row, block column); for P = (d, d) of the chain: i = d, c = d - 1
   int k0, k1;   // K blocks [k0, k1) of the tile's sum
