@@ -306,7 +306,9 @@ __device__ __forceinline__ void dmmaAcc(double& d0, double& d1, double a, double
 }
 template <int NR, int NC, int K, int UNROLL, bool HEAVY>
 __device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double* data, int64_t block) {
-  static_assert(NR <= 8 && NC <= 8 && K <= 4, "one m8n8k4 tile per task");
+  // blocks of up to 16 x 16 (e.g. 9-parameter cameras): MT x NT tiles of m8n8k4 per task, K <= 4 (the eliminated lump's width)
+  static_assert(NR <= 16 && NC <= 16 && K <= 4, "at most 2 x 2 m8n8k4 tiles per task");
+  constexpr int MT = (NR + 7) / 8, NT = (NC + 7) / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   // light destinations: a warp each; heavy ones (long task lists): the eight warps of a CTA take consecutive slices of
   // the list and their partial tiles are added in warp order
@@ -318,23 +320,33 @@ __device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double*
     if (w >= p.numLight) return;
     d = p.lightList[w];
   }
-  const bool onB = g < NR && t < K, onA = g < NC && t < K;
   const int idx = g * K + t;
   int tb = p.dstTaskPtr[d], te = p.dstTaskPtr[d + 1];
   // the destination's own entries are requested now, with the first tasks: one round trip less at the end
   double* dst = data + p.dstOff[d] + (int64_t)g * p.dstStride[d];
-  double old0 = 0.0, old1 = 0.0;
-  if (!HEAVY && g < NR) {
-    if (2 * t < NC) old0 = dst[2 * t];
-    if (2 * t + 1 < NC) old1 = dst[2 * t + 1];
-  }
+  const int64_t dstTile = 8 * (int64_t)p.dstStride[d];  // eight rows further down
+  double old[MT][NT][2];
+#pragma unroll
+  for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NT; ni++) {
+      old[mi][ni][0] = old[mi][ni][1] = 0.0;
+      if (!HEAVY && 8 * mi + g < NR) {
+        if (8 * ni + 2 * t < NC) old[mi][ni][0] = dst[mi * dstTile + 8 * ni + 2 * t];
+        if (8 * ni + 2 * t + 1 < NC) old[mi][ni][1] = dst[mi * dstTile + 8 * ni + 2 * t + 1];
+      }
+    }
   if (HEAVY) {
     const int chunk = (te - tb + 7) / 8;
     tb = min(te, tb + warp * chunk), te = min(te, tb + chunk);
   }
-  double c[UNROLL][2];
+  double c[UNROLL][MT][NT][2];
 #pragma unroll
-  for (int u = 0; u < UNROLL; u++) c[u][0] = c[u][1] = 0.0;
+  for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NT; ni++) c[u][mi][ni][0] = c[u][mi][ni][1] = 0.0;
   // the offsets of the next UNROLL tasks are fetched while the blocks of the current ones are in flight
   uint32_t oa[UNROLL], ob[UNROLL];
 #pragma unroll
@@ -343,40 +355,65 @@ __device__ __forceinline__ void elimGatherDmmaBody(const DevElimPlan& p, double*
     if (tb + u < te) oa[u] = __ldg(p.taskA + tb + u), ob[u] = __ldg(p.taskB + tb + u);
   }
   for (; tb < te; tb += UNROLL) {
-    double a[UNROLL], b[UNROLL];
+    double a[UNROLL][MT], b[UNROLL][NT];
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
-      const bool live = tb + u < te;
-      a[u] = onB && live ? data[ob[u] + idx] : 0.0;
-      b[u] = onA && live ? data[oa[u] + idx] : 0.0;
+      const bool live = tb + u < te && t < K;
+#pragma unroll
+      for (int mi = 0; mi < MT; mi++) a[u][mi] = live && 8 * mi + g < NR ? data[ob[u] + 8 * mi * K + idx] : 0.0;
+#pragma unroll
+      for (int ni = 0; ni < NT; ni++) b[u][ni] = live && 8 * ni + g < NC ? data[oa[u] + 8 * ni * K + idx] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; u++)
       if (tb + UNROLL + u < te) oa[u] = __ldg(p.taskA + tb + UNROLL + u), ob[u] = __ldg(p.taskB + tb + UNROLL + u);
     // a tile of zeros for a task beyond the end: adds nothing (the branch around an mma would only predicate it)
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) dmmaAcc(c[u][0], c[u][1], a[u], b[u]);
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NT; ni++) dmmaAcc(c[u][mi][ni][0], c[u][mi][ni][1], a[u][mi], b[u][ni]);
   }
 #pragma unroll
-  for (int u = 1; u < UNROLL; u++) c[0][0] += c[u][0], c[0][1] += c[u][1];
+  for (int u = 1; u < UNROLL; u++)
+#pragma unroll
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NT; ni++) c[0][mi][ni][0] += c[u][mi][ni][0], c[0][mi][ni][1] += c[u][mi][ni][1];
   if (HEAVY) {
-    __shared__ double red[8][32][2];
-    red[warp][lane][0] = c[0][0], red[warp][lane][1] = c[0][1];
+    __shared__ double red[8][MT * NT][32][2];
+#pragma unroll
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NT; ni++)
+        red[warp][mi * NT + ni][lane][0] = c[0][mi][ni][0], red[warp][mi * NT + ni][lane][1] = c[0][mi][ni][1];
     __syncthreads();
     if (warp != 0) return;
-    c[0][0] = red[0][lane][0], c[0][1] = red[0][lane][1];
 #pragma unroll
-    for (int w = 1; w < 8; w++) c[0][0] += red[w][lane][0], c[0][1] += red[w][lane][1];
+    for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NT; ni++) {
+        c[0][mi][ni][0] = red[0][mi * NT + ni][lane][0], c[0][mi][ni][1] = red[0][mi * NT + ni][lane][1];
+#pragma unroll
+        for (int w = 1; w < 8; w++)
+          c[0][mi][ni][0] += red[w][mi * NT + ni][lane][0], c[0][mi][ni][1] += red[w][mi * NT + ni][lane][1];
+      }
   }
-  if (g < NR) {
-    if (HEAVY) {
-      if (2 * t < NC) dst[2 * t] -= c[0][0];
-      if (2 * t + 1 < NC) dst[2 * t + 1] -= c[0][1];
-    } else {
-      if (2 * t < NC) dst[2 * t] = old0 - c[0][0];
-      if (2 * t + 1 < NC) dst[2 * t + 1] = old1 - c[0][1];
-    }
-  }
+#pragma unroll
+  for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NT; ni++)
+      if (8 * mi + g < NR) {
+        double* q = dst + mi * dstTile + 8 * ni + 2 * t;
+        if (HEAVY) {
+          if (8 * ni + 2 * t < NC) q[0] -= c[0][mi][ni][0];
+          if (8 * ni + 2 * t + 1 < NC) q[1] -= c[0][mi][ni][1];
+        } else {
+          if (8 * ni + 2 * t < NC) q[0] = old[mi][ni][0] - c[0][mi][ni][0];
+          if (8 * ni + 2 * t + 1 < NC) q[1] = old[mi][ni][1] - c[0][mi][ni][1];
+        }
+      }
 }
 // one launch: the first numHeavy CTAs take a heavy destination each (they are the long ones: first), the rest eight light
 // destinations each - the two parts share the SMs (stress workload: 1.21 ms against 1.34 for two launches)
@@ -936,6 +973,10 @@ void elimGather(cudaStream_t st, int batch, const DevElimPlan& plan, Mats<T> dat
       if (plan.uniRows == 3 && plan.uniCols == 3 && plan.uniK == 3)
         return shortLists ? launchParts(elim_gather_dmma_part_kernel<3, 3, 3, 1, false>, elim_gather_dmma_part_kernel<3, 3, 3, 4, true>)
                           : launch(elim_gather_dmma_kernel<3, 3, 3, 4, 4>);
+      // 9-parameter cameras (pose + intrinsics: the camera model of the BAL data sets) with 3-d points: 2 x 2 tiles per task
+      if (plan.uniRows == 9 && plan.uniCols == 9 && plan.uniK == 3)
+        return shortLists ? launchParts(elim_gather_dmma_part_kernel<9, 9, 3, 1, false>, elim_gather_dmma_part_kernel<9, 9, 3, 2, true>)
+                          : launch(elim_gather_dmma_kernel<9, 9, 3, 2, 2>);
     }
   }
   // BSPB200_GATHER=5: 16-byte operand loads for the light list (fp64, 6x6x3), staged kernel for the heavy list

@@ -329,15 +329,16 @@ def _oracle_pair(sizes, ptrs, inds, ranges, **kw):
 
 
 @pytest.mark.parametrize("mode", ["1", "6"])
-@pytest.mark.parametrize("batch", [1, 3])
-def test_elimination_gather_variants_match_oracle_and_are_deterministic(mode, batch, monkeypatch):
+@pytest.mark.parametrize("batch,cam_size", [(1, 6), (3, 6), (1, 9), (2, 9)])
+def test_elimination_gather_variants_match_oracle_and_are_deterministic(mode, batch, cam_size, monkeypatch):
     """The two shipped gathers of the sparse elimination - per-lane SIMT (BSPB200_GATHER=1) and one DMMA per block pair
     (=6, the fp64 default; reference kernel replaced: MatOpsCuda.cu:235-331, atomics there) - on a bundle-adjustment-
     shaped problem with long and short task lists, single and batched: each matches the CPU oracle within the stated
     tolerance and gives the same bits twice (fixed summation order, no atomics)."""
     import torch
     monkeypatch.setenv("BSPB200_GATHER", mode)
-    sizes, ptrs, inds = H.ba_problem(6000, 40, seed=11)
+    # cam_size 9 = pose + intrinsics (the camera model of the BAL data sets): 2 x 2 DMMA tiles per block pair
+    sizes, ptrs, inds = H.ba_problem(6000, 40, seed=11, cam_size=cam_size)
     g, o = _oracle_pair(sizes, ptrs, inds, [0, 6000], find_sparse_elim_ranges=True)
     mask = H.flat_lower_mask(g)
     datas = [H.make_data(g, 50 + b, np.float64, 1.3) for b in range(batch)]
