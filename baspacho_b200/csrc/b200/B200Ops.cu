@@ -1228,6 +1228,19 @@ struct B200SolveCtx : SolveCtx<TT> {
     elimSolveLt<T>(sym.stream, m.batch, sym.dsk, elim->dev, m, v, ldc, nRHS);
   }
 
+  // addMvFrom over a whole sparse-elimination range in two launches (MatOps.h addition; the reference walks the lumps)
+  bool hasSparseElimMV() override {
+    static const bool on = !getenv("BSPB200_SPARSE_MV") || atoi(getenv("BSPB200_SPARSE_MV")) != 0;
+    return on;
+  }
+  void sparseElimMV(const SymElimCtx& elimData, const TT* data, const TT* in, int64_t inStride, TT* out, int64_t outStride,
+                    T alpha) override {
+    const auto* elim = dynamic_cast<const B200SymElimCtx*>(&elimData);
+    BASPACHO_CHECK_NOTNULL(elim);
+    Mats<T> m = mats.get(data, sym.stream), x = vecs.get(in, sym.stream), y = vecs2.get(out, sym.stream);
+    elimMV<T>(sym.stream, m.batch, sym.dsk, elim->dev, m, x, inStride, y, outStride, nRHS, alpha);
+  }
+
   void symm(const TT* data, int64_t offM, int64_t n, const TT* C, int64_t offC, int64_t ldc, TT* D, int64_t ldd,
             T alpha) override {
     auto timer = sym.symmStat.template instance<B200SyncOps>();

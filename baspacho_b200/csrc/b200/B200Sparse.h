@@ -92,6 +92,11 @@ void assemble(cudaStream_t st, int batch, const DevSkel& sk, const int64_t* span
 template <typename T>
 void elimSolveL(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> C,
                 int64_t ldc, int nRHS);
+// out += alpha * A * in over the columns of the elimination range (both triangles of the symmetric matrix)
+template <typename T>
+void elimMV(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> in, int64_t ldi,
+            Mats<T> out, int64_t ldo, int nRHS, T alpha);
+
 template <typename T>
 void elimSolveLt(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> C,
                  int64_t ldc, int nRHS);

@@ -1089,6 +1089,104 @@ void elimSolveLt(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPla
   B200_LAUNCH_CHECK();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// out += alpha * A * in over the columns of a sparse-elimination range (addMvFrom; A symmetric, lower blocks stored).
+// (1) column pass, thread per (lump, rhs): out_l += alpha (D_l in_l + sum over the lump's chains of B^T in[rows]) - each
+//     lump owns its output; (2) row pass, CTA per row span below the range: out[span] += alpha sum over the span's chains
+//     of B in_l - the row view of the elimination plan, fixed order, no atomics.
+template <typename T>
+__global__ void __launch_bounds__(128) elim_mv_cols_kernel(DevSkel sk, Mats<T> mats, Mats<T> inV, int64_t ldi, Mats<T> outV,
+                                                           int64_t ldo, int nRHS, int64_t lumpsBegin, int64_t lumpsEnd,
+                                                           T alpha) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t lump = lumpsBegin + gid / nRHS;
+  if (lump >= lumpsEnd) return;
+  const int rhs = (int)(gid % nRHS);
+  const T* __restrict__ data = mats.at(blockIdx.z);
+  const T* __restrict__ X = inV.at(blockIdx.z) + (int64_t)rhs * ldi;
+  T* Y = outV.at(blockIdx.z) + (int64_t)rhs * ldo;
+  const int s = (int)(sk.lumpStart[lump + 1] - sk.lumpStart[lump]);
+  const int64_t c0 = sk.lumpStart[lump];
+  const T* __restrict__ D = data + sk.chainData[sk.chainColPtr[lump]];
+  const int64_t first = sk.chainColPtr[lump] + (sk.lumpToSpan[lump + 1] - sk.lumpToSpan[lump]);
+  const int64_t end = sk.chainColPtr[lump + 1];
+  for (int q = 0; q < s; q++) {
+    T acc = 0;
+    for (int j = 0; j < s; j++) acc += (j <= q ? D[q * s + j] : D[j * s + q]) * X[c0 + j];
+    for (int64_t ch = first; ch < end; ch++) {
+      const int64_t span = sk.chainRowSpan[ch];
+      const int64_t r0 = sk.spanStart[span];
+      const int rows = (int)(sk.spanStart[span + 1] - r0);
+      const T* __restrict__ blk = data + sk.chainData[ch];
+      for (int r = 0; r < rows; r++) acc += blk[r * s + q] * X[r0 + r];
+    }
+    Y[c0 + q] += alpha * acc;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) elim_mv_rows_kernel(DevSkel sk, DevElimPlan p, Mats<T> mats, Mats<T> inV, int64_t ldi,
+                                                           Mats<T> outV, int64_t ldo, int nRHS, int E, T alpha) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* red = reinterpret_cast<T*>(smemRaw);
+  const int64_t rel = blockIdx.x;
+  const int cBegin = p.rowPtr[rel], cEnd = p.rowPtr[rel + 1];
+  if (cBegin == cEnd) return;
+  const int64_t span = rel + p.spanRowBegin;
+  const int64_t r0 = sk.spanStart[span];
+  const int rows = (int)(sk.spanStart[span + 1] - r0);
+  const T* __restrict__ data = mats.at(blockIdx.z);
+  const T* __restrict__ X = inV.at(blockIdx.z);
+  T* Y = outV.at(blockIdx.z);
+  const int G = blockDim.x / E;
+  const int e = threadIdx.x % E, g = threadIdx.x / E;
+  const int nElems = rows * nRHS;
+  for (int e0 = 0; e0 < nElems; e0 += E) {
+    const int el = e0 + e;
+    T acc = 0;
+    if (el < nElems && g < G) {
+      const int r = el % rows, rhs = el / rows;
+      for (int c = cBegin + g; c < cEnd; c += G) {
+        const int k = p.rowChainK[c];
+        const T* __restrict__ blk = data + p.rowChainOff[c] + r * k;
+        const T* __restrict__ x = X + (int64_t)rhs * ldi + p.rowChainCol[c];
+        for (int q = 0; q < k; q++) acc += blk[q] * x[q];
+      }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0 && el < nElems) {
+      T tot = 0;
+      for (int gg = 0; gg < G; gg++) tot += red[gg * E + e];
+      const int r = el % rows, rhs = el / rows;
+      Y[(int64_t)rhs * ldo + r0 + r] += alpha * tot;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+void elimMV(cudaStream_t st, int batch, const DevSkel& sk, const DevElimPlan& plan, Mats<T> data, Mats<T> in, int64_t ldi,
+            Mats<T> out, int64_t ldo, int nRHS, T alpha) {
+  const int64_t n = (plan.lumpsEnd - plan.lumpsBegin) * nRHS;
+  if (n <= 0) return;
+  ProfScope prof(st, KC_SOLVE_ELIM, 0, plan.factorEntries * sizeof(T) * batch * 2);
+  // the row pass first: it reads in[range] and writes out[below]; the column pass writes out[range] - with in == out
+  // aliasing excluded by the interface (addMvFrom takes distinct vectors) the order does not matter
+  if (plan.numRowSpans > 0) {
+    int elems = plan.maxRowSpanSize * nRHS;
+    int E = 1;
+    while (E < elems && E < 32) E *= 2;
+    elim_mv_rows_kernel<T><<<dim3((unsigned)plan.numRowSpans, 1, batch), 256, 256 * sizeof(T), st>>>(sk, plan, data, in, ldi, out,
+                                                                                                     ldo, nRHS, E, alpha);
+    B200_LAUNCH_CHECK();
+  }
+  elim_mv_cols_kernel<T><<<dim3(ceilDiv(n, 128), 1, batch), 128, 0, st>>>(sk, data, in, ldi, out, ldo, nRHS, plan.lumpsBegin,
+                                                                          plan.lumpsEnd, alpha);
+  B200_LAUNCH_CHECK();
+}
+
 template <typename T>
 void assembleVec(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, int64_t chainColPtr, int64_t numColItems,
                  int64_t numRows, Mats<T> C, int64_t ldc, int nRHS) {
@@ -1117,6 +1215,8 @@ void assembleVecT(cudaStream_t st, int batch, const DevSkel& sk, Work<T> tmp, in
                             int64_t, int64_t, int64_t, int64_t, int64_t);                                               \
   template void elimSolveL<T>(cudaStream_t, int, const DevSkel&, const DevElimPlan&, Mats<T>, Mats<T>, int64_t, int);  \
   template void elimSolveLt<T>(cudaStream_t, int, const DevSkel&, const DevElimPlan&, Mats<T>, Mats<T>, int64_t, int); \
+  template void elimMV<T>(cudaStream_t, int, const DevSkel&, const DevElimPlan&, Mats<T>, Mats<T>, int64_t, Mats<T>,   \
+                          int64_t, int, T);                                                                            \
   template void assembleVec<T>(cudaStream_t, int, const DevSkel&, Work<T>, int64_t, int64_t, int64_t, Mats<T>,         \
                                int64_t, int);                                                                           \
   template void assembleVecT<T>(cudaStream_t, int, const DevSkel&, Work<T>, int64_t, int64_t, int64_t, Mats<T>,        \

@@ -142,6 +142,14 @@ struct SolveCtx : SolveCtxBase {
                      int64_t lda, BaseType<T> alpha) = 0;
   virtual void assembleVecT(const T* C, int64_t ldc, int64_t chainColPtr, int64_t numColItems) = 0;
 
+  // optional (B200 backend, round 2): out += alpha * A * in restricted to the COLUMNS of one sparse-elimination range -
+  // diagonal blocks, the blocks below them and their transposes - in two launches instead of five per lump. The
+  // reference's addMvFrom walks every lump ("sparse ops not supported yet", Solver.cpp:408-446).
+  virtual bool hasSparseElimMV() { return false; }
+  virtual void sparseElimMV(const SymElimCtx&, const T*, const T*, int64_t, T*, int64_t, BaseType<T>) {
+    throw std::runtime_error("sparseElimMV: not supported");
+  }
+
   virtual bool hasFragmentedOps() { return false; }
   virtual void fragmentedMV(const T*, const T*, int64_t, int64_t, T*, BaseType<T>) {
     throw std::runtime_error("fragmentedMV: not supported");

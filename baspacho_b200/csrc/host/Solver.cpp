@@ -342,7 +342,17 @@ void Solver::addMvFrom(const T* matData, int64_t spanIndex, const T* inVecData, 
     slvCtx->fragmentedMV(matData, inVecData, fromLump, nLumps, outVecData, alpha);
     return;
   }
+  // whole sparse-elimination ranges at or behind the start: one backend call each when the backend offers it
+  int64_t skipBegin = -1, skipEnd = -1;  // the ranges are contiguous from lump sparseElimRanges[0] on: one skipped interval
+  if (slvCtx->hasSparseElimMV())
+    for (size_t r = 0; r + 1 < sparseElimRanges.size(); r++) {
+      if (sparseElimRanges[r] < fromLump) continue;
+      slvCtx->sparseElimMV(*elimCtxs[r], matData, inVecData, inStride, outVecData, outStride, alpha);
+      if (skipBegin < 0) skipBegin = sparseElimRanges[r];
+      skipEnd = sparseElimRanges[r + 1];
+    }
   for (int64_t l = fromLump; l < nLumps; l++) {
+    if (l >= skipBegin && l < skipEnd) continue;
     ColumnGeom g = columnGeom(l);
     slvCtx->symm(matData, g.diagOffset, g.size, inVecData, g.start, inStride, outVecData, outStride, alpha);
     if (g.rowsBelow == 0) continue;

@@ -249,6 +249,32 @@ def test_add_mv_and_pseudo_factor(dtype):
         assert np.abs(d.cpu().numpy() - ref).max() <= H.ORACLE_RTOL[dtype] * 20 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_add_mv_over_sparse_elimination_ranges(dtype):
+    """addMvFrom started inside / in front of sparse-elimination ranges: the backend's two-launch product over a whole
+    range (MatOps.h sparseElimMV; the reference walks the lumps, Solver.cpp:408-446) against dense algebra on the
+    densified matrix, from span 0 (both ranges in one go), from the second range, and from the dense part; three
+    right-hand sides, alpha != 1, output accumulated onto a non-zero vector."""
+    n_pts = 420
+    sizes, ptrs, inds = H.ba_problem(n_pts, 14, seed=9, window=4)
+    g, o = make_pair(sizes, ptrs, inds, [0, 200, n_pts])
+    assert g.num_elim_ranges >= 2
+    data = H.make_data(g, 4, dtype)
+    A = H.sym_from_lower(g.densify(data)).astype(np.float64)
+    rhs = H.oapi().random_data_array(g.order * 3, -1, 1, 15, dtype=dtype).reshape(3, g.order)
+    out0 = H.oapi().random_data_array(g.order * 3, -1, 1, 16, dtype=dtype).reshape(3, g.order)
+    ranges = g.sparseElimRanges
+    for cut_lump in (0, int(ranges[1]), int(ranges[-1])):
+        cut = int(g.lumpToSpan[cut_lump])
+        x, y = torch_of(rhs), torch_of(out0)
+        g.add_mv_from(torch_of(data), cut, x, y, alpha=-1.3)
+        r0 = int(g.spanStart[cut])
+        exp = out0.astype(np.float64).T.copy()
+        exp[r0:] += -1.3 * (A[r0:, r0:] @ rhs.astype(np.float64).T[r0:])
+        err = np.linalg.norm(y.cpu().numpy().astype(np.float64).T - exp) / np.linalg.norm(exp)
+        assert err < (1e-13 if dtype == np.float64 else 1e-5), (cut_lump, err)
+
+
 def test_factor_solve_host_end_to_end():
     """the host-buffer entry point bench.py's e2e leg times: H2D, factor, solve, D2H"""
     n_pts = 400
